@@ -1,0 +1,283 @@
+// oracle_capi.cpp -- C entry points over lyon_oracle.hpp for ctypes (tests, smoke, bench cpu_baseline).
+// TEST INFRASTRUCTURE ONLY: nothing under lyon_b200/ may link or load this library.
+//
+// Batch semantics follow SURVEY §8(b): a batch is `for p in paths { StrokeTessellator::new()
+// .tessellate_path(p, opts, &mut BuffersBuilder::new(&mut out, ctor)) }` on ONE VertexBuffers, so
+// vertex ids are absolute (geometry_builder.rs:342-349).
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <thread>
+
+#include "lyon_oracle.hpp"
+
+using namespace lyon_oracle;
+
+struct oracle_mesh {
+    Buffers buf;
+    std::vector<uint64_t> path_vertex_end;  // per path: vertices.size() after the path
+    std::vector<uint64_t> path_index_end;
+};
+
+extern "C" {
+
+// Stroke a batch on one thread into one buffer. Returns 0 or a negative error (first failing path aborts the batch).
+// max_index: largest vertex id that may be handed out (0xFFFFFFFE for u32 buffers).
+oracle_mesh* oracle_stroke_batch(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                                 const uint32_t* path_point_begin, uint32_t n_paths, uint32_t num_attributes,
+                                 const Options* opts, uint64_t max_index, int* err) {
+    oracle_mesh* m = new oracle_mesh();
+    m->buf.max_index = max_index;
+    *err = OK;
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        uint32_t vb = path_verb_begin[p], ve = path_verb_begin[p + 1];
+        int e = stroke_path(verbs + vb, ve - vb, points + 2 * (size_t)path_point_begin[p], num_attributes, *opts, m->buf);
+        if (e != OK) {
+            *err = e;
+            // tessellate_paths returns Err: nothing is handed back.
+            m->buf.vertices.clear();
+            m->buf.indices.clear();
+            m->path_vertex_end.clear();
+            m->path_index_end.clear();
+            return m;
+        }
+        m->path_vertex_end.push_back(m->buf.vertices.size());
+        m->path_index_end.push_back(m->buf.indices.size());
+    }
+    return m;
+}
+uint64_t oracle_mesh_num_vertices(const oracle_mesh* m) { return m->buf.vertices.size(); }
+uint64_t oracle_mesh_num_indices(const oracle_mesh* m) { return m->buf.indices.size(); }
+void oracle_mesh_copy(const oracle_mesh* m, void* vertices, uint32_t* indices, uint64_t* path_vertex_end,
+                      uint64_t* path_index_end) {
+    if (vertices) memcpy(vertices, m->buf.vertices.data(), m->buf.vertices.size() * sizeof(Vertex));
+    if (indices) memcpy(indices, m->buf.indices.data(), m->buf.indices.size() * sizeof(uint32_t));
+    if (path_vertex_end) memcpy(path_vertex_end, m->path_vertex_end.data(), m->path_vertex_end.size() * 8);
+    if (path_index_end) memcpy(path_index_end, m->path_index_end.data(), m->path_index_end.size() * 8);
+}
+void oracle_mesh_free(oracle_mesh* m) { delete m; }
+
+// Timed multi-threaded run for the CPU baseline ("rayon-parallel over paths" stand-in): paths are
+// handed out in blocks to n_threads workers, each tessellating into its own pre-reserved buffers
+// (as bench/tess pre-sizes its VertexBuffers).  Returns seconds of wall clock for the parallel
+// region only; writes total vertices / indices produced.
+double oracle_stroke_batch_timed(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                                 const uint32_t* path_point_begin, uint32_t n_paths, uint32_t num_attributes,
+                                 const Options* opts, int n_threads, uint64_t* total_vertices,
+                                 uint64_t* total_indices) {
+    if (n_threads < 1) n_threads = 1;
+    std::vector<Buffers> bufs((size_t)n_threads);
+    // Pre-reserve from a one-path probe (outside the timed region).
+    size_t probe_v = 64, probe_i = 192;
+    if (n_paths > 0) {
+        Buffers probe;
+        stroke_path(verbs + path_verb_begin[0], path_verb_begin[1] - path_verb_begin[0],
+                    points + 2 * (size_t)path_point_begin[0], num_attributes, *opts, probe);
+        probe_v = probe.vertices.size() * 5 / 4 + 64;
+        probe_i = probe.indices.size() * 5 / 4 + 192;
+    }
+    size_t per_thread = (size_t)n_paths / (size_t)n_threads + 1;
+    for (auto& b : bufs) {
+        b.vertices.reserve(per_thread * probe_v);
+        b.indices.reserve(per_thread * probe_i);
+    }
+    std::atomic<uint32_t> next(0);
+    const uint32_t block = 256;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) {
+        th.emplace_back([&, t]() {
+            Buffers& b = bufs[(size_t)t];
+            for (;;) {
+                uint32_t s = next.fetch_add(block);
+                if (s >= n_paths) break;
+                uint32_t e = s + block < n_paths ? s + block : n_paths;
+                for (uint32_t p = s; p < e; ++p) {
+                    uint32_t vb = path_verb_begin[p], ve = path_verb_begin[p + 1];
+                    stroke_path(verbs + vb, ve - vb, points + 2 * (size_t)path_point_begin[p], num_attributes, *opts, b);
+                }
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    uint64_t tv = 0, ti = 0;
+    for (auto& b : bufs) {
+        tv += b.vertices.size();
+        ti += b.indices.size();
+    }
+    *total_vertices = tv;
+    *total_indices = ti;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- flattening -------------------------------------------------------------------------------
+// Flatten a batch of standalone cubic segments (ctrl = 8 floats per curve: from, ctrl1, ctrl2, to), the
+// point sequence of CubicBezierSegment::for_each_flattened (cubic_bezier.rs:563-582): for each curve the
+// points AFTER `from`.  offsets_out has n+1 entries.  If points_out is NULL only offsets are written.
+void oracle_flatten_cubics(const float* ctrl, uint64_t n, float tol, uint64_t* offsets_out, float* points_out,
+                           float* t_out) {
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* c = ctrl + 8 * i;
+        offsets_out[i] = off;
+        cubic_for_each_flattened_with_t(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol,
+                                        [&](V2 p, float t) {
+                                            if (points_out) {
+                                                points_out[2 * off] = p.x;
+                                                points_out[2 * off + 1] = p.y;
+                                            }
+                                            if (t_out) t_out[off] = t;
+                                            off++;
+                                        });
+    }
+    offsets_out[n] = off;
+}
+// Same for quadratic segments (ctrl = 6 floats per curve), QuadraticBezierSegment::for_each_flattened
+// (quadratic_bezier.rs:337-360).
+void oracle_flatten_quadratics(const float* ctrl, uint64_t n, float tol, uint64_t* offsets_out, float* points_out,
+                               float* t_out) {
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* c = ctrl + 6 * i;
+        offsets_out[i] = off;
+        quad_for_each_flattened_with_t(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol, [&](V2 p, float t) {
+            if (points_out) {
+                points_out[2 * off] = p.x;
+                points_out[2 * off + 1] = p.y;
+            }
+            if (t_out) t_out[off] = t;
+            off++;
+        });
+    }
+    offsets_out[n] = off;
+}
+double oracle_flatten_cubics_timed(const float* ctrl, uint64_t n, float tol, int n_threads, float* points_out,
+                                   const uint64_t* offsets, uint64_t* total) {
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint64_t> next(0);
+    std::atomic<uint64_t> tot(0);
+    const uint64_t block = 4096;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) {
+        th.emplace_back([&]() {
+            uint64_t local = 0;
+            for (;;) {
+                uint64_t s = next.fetch_add(block);
+                if (s >= n) break;
+                uint64_t e = s + block < n ? s + block : n;
+                for (uint64_t i = s; i < e; ++i) {
+                    const float* c = ctrl + 8 * i;
+                    uint64_t off = offsets[i];
+                    cubic_for_each_flattened_with_t(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]),
+                                                    tol, [&](V2 p, float) {
+                                                        points_out[2 * off] = p.x;
+                                                        points_out[2 * off + 1] = p.y;
+                                                        off++;
+                                                        local++;
+                                                    });
+                }
+            }
+            tot += local;
+        });
+    }
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    *total = tot.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Path-level flattening (crates/path/src/iterator.rs:150-207 `Flattened`): every curve event becomes
+// the line_to sequence of its flattened points; Begin/Line/End/Close pass through.  Works on paths
+// WITHOUT custom attributes.  Output verbs/points use the same encoding as the input.
+// out arrays must be large enough (call once with NULL outputs to get the sizes).
+void oracle_flatten_paths(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                          const uint32_t* path_point_begin, uint32_t n_paths, float tol, uint8_t* out_verbs,
+                          float* out_points, uint32_t* out_path_verb_begin, uint32_t* out_path_point_begin,
+                          uint64_t* n_out_verbs, uint64_t* n_out_points) {
+    uint64_t ov = 0, op = 0;
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        if (out_path_verb_begin) out_path_verb_begin[p] = (uint32_t)ov;
+        if (out_path_point_begin) out_path_point_begin[p] = (uint32_t)op;
+        const float* pts = points + 2 * (size_t)path_point_begin[p];
+        uint32_t cur = 0;
+        V2 current = v2(0, 0), first = v2(0, 0);
+        auto P = [&](uint32_t i) { return v2(pts[2 * i], pts[2 * i + 1]); };
+        auto emit = [&](uint8_t verb, bool has_pt, V2 pt) {
+            if (out_verbs) out_verbs[ov] = verb;
+            ov++;
+            if (has_pt) {
+                if (out_points) {
+                    out_points[2 * op] = pt.x;
+                    out_points[2 * op + 1] = pt.y;
+                }
+                op++;
+            }
+        };
+        for (uint32_t vi = path_verb_begin[p]; vi < path_verb_begin[p + 1]; ++vi) {
+            switch (verbs[vi]) {
+                case 3:
+                    current = first = P(cur++);
+                    emit(3, true, current);
+                    break;
+                case 0:
+                    current = P(cur++);
+                    emit(0, true, current);
+                    break;
+                case 1: {
+                    V2 c = P(cur), to = P(cur + 1);
+                    cur += 2;
+                    quad_for_each_flattened_with_t(current, c, to, tol, [&](V2 q, float) { emit(0, true, q); });
+                    current = to;
+                    break;
+                }
+                case 2: {
+                    V2 c1 = P(cur), c2 = P(cur + 1), to = P(cur + 2);
+                    cur += 3;
+                    cubic_for_each_flattened_with_t(current, c1, c2, to, tol, [&](V2 q, float) { emit(0, true, q); });
+                    current = to;
+                    break;
+                }
+                case 4:
+                    cur += 1;
+                    emit(4, true, first);
+                    current = first;
+                    break;
+                case 5:
+                    emit(5, false, first);
+                    current = first;
+                    break;
+            }
+        }
+    }
+    if (out_path_verb_begin) out_path_verb_begin[n_paths] = (uint32_t)ov;
+    if (out_path_point_begin) out_path_point_begin[n_paths] = (uint32_t)op;
+    *n_out_verbs = ov;
+    *n_out_points = op;
+}
+
+// ---- small pure functions exposed for known-answer tests ----------------------------------------
+void oracle_compute_normal(float v1x, float v1y, float v2x, float v2y, float* out) {
+    V2 n = compute_normal(v2(v1x, v1y), v2(v2x, v2y));
+    out[0] = n.x;
+    out[1] = n.y;
+}
+float oracle_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+float oracle_angle_to(float a, float b) { return angle_to(a, b); }
+float oracle_cubic_wang(const float* c, float tol) {
+    return cubic_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol);
+}
+float oracle_quad_wang(const float* c, float tol) { return quad_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol); }
+int oracle_find_sharp_turn(const float* c, float* t) {
+    return find_sharp_turn(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), t) ? 1 : 0;
+}
+float oracle_circle_flattening_step(float r, float tol) { return circle_flattening_step(r, tol); }
+int oracle_line_intersection(const float* a, const float* b, float* out) {
+    V2 o = v2(0.0f, 0.0f);
+    bool ok = line_intersection(line_d(v2(a[0], a[1]), v2(a[2], a[3])), line_d(v2(b[0], b[1]), v2(b[2], b[3])), &o);
+    out[0] = o.x;
+    out[1] = o.y;
+    return ok ? 1 : 0;
+}
+}  // extern "C"
