@@ -1,0 +1,139 @@
+/* lyon_cuda.h -- C ABI of the B200-native batched path flattener and stroke tessellator.
+ *
+ * This is the drop-in boundary for lyon's data-parallel hot path.  Nothing like
+ * it exists in the reference (lyon is single-process Rust); each entry point names the reference
+ * interface it stands in for (file:line under nical/lyon @ 8071ec06).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - A context owns one CUDA device, one stream and a grow-only workspace; it is externally
+ *     synchronised (like `&mut StrokeTessellator`, stroke.rs:122-127).  Distinct contexts are independent.
+ *   - All functions return LYON_OK (0) or a negative lyon_status.  On error output counts are 0
+ *     (the reference rolls its buffers back with abort_geometry, geometry_builder.rs:478-481).
+ *   - Pointers named d_* are DEVICE pointers; h_* are HOST pointers.
+ *   - There is no CPU fallback: without a CUDA device lyon_cuda_create fails.
+ */
+#ifndef LYON_CUDA_H
+#define LYON_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lyon_cuda_ctx lyon_cuda_ctx;
+
+typedef enum {
+    LYON_OK = 0,
+    LYON_ERR_UNSUPPORTED_PARAMETER = -1, /* TessellationError::UnsupportedParamater (error.rs) */
+    LYON_ERR_TOO_MANY_VERTICES = -2,     /* GeometryBuilderError::TooManyVertices (geometry_builder.rs:342-346) */
+    LYON_ERR_INTERNAL = -3,              /* TessellationError::Internal */
+    LYON_ERR_CUDA = -4,                  /* CUDA runtime failure (no reference analogue) */
+    LYON_ERR_INVALID_ARGUMENT = -5,
+    LYON_ERR_OUT_OF_MEMORY = -6
+} lyon_status;
+
+/* Path verbs, the encoding of lyon_path's private `Verb` (crates/path/src/path.rs:29-36). */
+enum { LYON_VERB_LINE_TO = 0, LYON_VERB_QUADRATIC_TO = 1, LYON_VERB_CUBIC_TO = 2, LYON_VERB_BEGIN = 3, LYON_VERB_CLOSE = 4, LYON_VERB_END = 5 };
+/* LineCap / LineJoin in declaration order (crates/path/src/lib.rs:170-174, :193-198). */
+enum { LYON_CAP_BUTT = 0, LYON_CAP_SQUARE = 1, LYON_CAP_ROUND = 2 };
+enum { LYON_JOIN_MITER = 0, LYON_JOIN_MITER_CLIP = 1, LYON_JOIN_ROUND = 2, LYON_JOIN_BEVEL = 3 };
+
+/* #[repr(C)] mirror of StrokeOptions (crates/tessellation/src/lib.rs:315-353). */
+typedef struct {
+    uint8_t start_cap, end_cap, line_join, _pad;
+    float line_width;
+    int32_t variable_line_width; /* Option<AttributeIndex>: -1 = None */
+    float miter_limit;
+    float tolerance;
+} lyon_stroke_options;
+
+/* StrokeVertexGpu: everything lyon's StrokeVertex exposes (stroke.rs:2656-2747), 32 bytes, 16-byte aligned.
+ *   position()  = position_on_path + normal * half_width      (stroke.rs:2676-2678)
+ *   side        = (src & 0x80000000) ? Side::Negative : Side::Positive
+ *   source      = t == 1.0 ? VertexSource::Endpoint{ id: src & 0x7fffffff }
+ *                          : VertexSource::Edge{ to: src & 0x7fffffff, t }   (lib.rs:282-291)          */
+typedef struct {
+    float position_on_path[2];
+    float normal[2];
+    float advancement;
+    float half_width;
+    uint32_t src;
+    float t;
+} lyon_stroke_vertex;
+
+/* A batch of paths in lyon_path's own storage layout, concatenated (path.rs:75-79; PathBuffer,
+ * path_buffer.rs:15-27): verbs[u8], points[f32 xy pairs incl. control points and, after every endpoint,
+ * ceil(num_attributes/2) attribute slots], and N+1 begin offsets per path (in verbs / in points). */
+typedef struct {
+    const uint8_t* verbs;
+    const float* points;
+    const uint32_t* path_verb_begin;
+    const uint32_t* path_point_begin;
+    uint32_t n_paths;
+    uint32_t num_attributes;
+    uint32_t n_verbs;  /* == path_verb_begin[n_paths]; path_verb_begin[0] must be 0 */
+    uint32_t n_points; /* == path_point_begin[n_paths]; path_point_begin[0] must be 0 */
+} lyon_path_batch;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* `stream` may be NULL (the context creates its own) or an existing cudaStream_t to launch on. */
+int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out);
+void lyon_cuda_destroy(lyon_cuda_ctx* ctx);
+int lyon_cuda_set_stream(lyon_cuda_ctx* ctx, void* stream);
+int lyon_cuda_synchronize(lyon_cuda_ctx* ctx);
+const char* lyon_cuda_last_error(const lyon_cuda_ctx* ctx);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t lyon_cuda_launch_count(const lyon_cuda_ctx* ctx);
+/* Bytes currently held by the context's workspace. */
+uint64_t lyon_cuda_workspace_bytes(const lyon_cuda_ctx* ctx);
+
+/* ---- curve flattening (lyon_geom) ------------------------------------------------------------------ */
+/* Batched CubicBezierSegment::for_each_flattened / ::flattened(tolerance) (cubic_bezier.rs:563-614,
+ * 1405-1454).  d_ctrl: n x 8 floats (from, ctrl1, ctrl2, to).  Pass 1 counts: d_offsets (n+1 u64, device)
+ * receives the exclusive scan of per-curve point counts; *total_points (host) the grand total. */
+int lyon_cuda_flatten_cubics_count(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance,
+                                   uint64_t* d_offsets, uint64_t* total_points);
+/* Pass 2 emits the points after `from` of every curve, curve after curve, into d_points (xy pairs);
+ * d_t (may be NULL) receives the curve parameter of each point (for_each_flattened_with_t). */
+int lyon_cuda_flatten_cubics_emit(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance,
+                                  const uint64_t* d_offsets, uint64_t total_points, float* d_points, float* d_t);
+/* Same for QuadraticBezierSegment (quadratic_bezier.rs:337-391, 979-1031). d_ctrl: n x 6 floats. */
+int lyon_cuda_flatten_quadratics_count(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance,
+                                       uint64_t* d_offsets, uint64_t* total_points);
+int lyon_cuda_flatten_quadratics_emit(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance,
+                                      const uint64_t* d_offsets, uint64_t total_points, float* d_points, float* d_t);
+
+/* ---- stroke tessellation (lyon_tessellation::StrokeTessellator) ------------------------------------ */
+/* Equivalent of, for every path p of the batch in order,
+ *     StrokeTessellator::new().tessellate_path(p, options, &mut BuffersBuilder::new(&mut out, ctor))
+ * (stroke.rs:164-177) on ONE VertexBuffers<StrokeVertexGpu, u32>, i.e. indices are absolute
+ * (geometry_builder.rs:342-349).
+ *
+ * Step 1, plan: uploads nothing; `batch` pointers are DEVICE pointers.  Runs the count passes and the
+ * scans and returns the exact output sizes.  Fails with LYON_ERR_TOO_MANY_VERTICES when
+ * vertex_base + n_vertices - 1 > u32::MAX - 1. */
+int lyon_cuda_stroke_plan(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, const lyon_stroke_options* options,
+                          uint64_t* n_vertices, uint64_t* n_indices);
+/* Step 2, emit: writes n_vertices vertices and n_indices u32 indices of the planned batch.
+ * vertex_base is added to every index (BuffersBuilder::with_vertex_offset, geometry_builder.rs:325-329;
+ * multi-GPU global rebasing).  d_path_vertex_end / d_path_index_end (may be NULL): per path, the vertex /
+ * index count of the batch up to and including that path (u64, relative to this batch). */
+int lyon_cuda_stroke_emit(lyon_cuda_ctx* ctx, lyon_stroke_vertex* d_vertices, uint32_t* d_indices,
+                          uint64_t vertex_base, uint64_t* d_path_vertex_end, uint64_t* d_path_index_end);
+
+/* Synchronises and reads back the device-side consistency flag of the last emit: LYON_ERR_INTERNAL if the
+ * emit pass ever produced a different number of vertices/triangles for a slot than the count pass planned. */
+int lyon_cuda_check(lyon_cuda_ctx* ctx);
+
+/* Host-buffer convenience (what a lyon user calls): upload the batch, plan, allocate, emit, download.
+ * *h_vertices / *h_indices are malloc'ed by the library (free with lyon_cuda_free_host). */
+int lyon_cuda_tessellate_paths(lyon_cuda_ctx* ctx, const lyon_path_batch* h_batch,
+                               const lyon_stroke_options* options, lyon_stroke_vertex** h_vertices,
+                               uint64_t* n_vertices, uint32_t** h_indices, uint64_t* n_indices);
+void lyon_cuda_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LYON_CUDA_H */

@@ -1,0 +1,782 @@
+// lyon_cuda.cu -- CUDA kernels (sm_100a) and the C ABI of include/lyon_cuda.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see __graft_entry__.build()).
+// -fmad=false is part of the numerical contract: lyon (rustc) never contracts a*b+c, and vertex/index
+// topology depends on f32 compares of such expressions (hard part 1).
+//
+// Kernel inventory (the per-item logic lives in stroke_core.cuh / device_math.cuh):
+//   k_seg_setup     1 thread / verb        two chained decoupled-look-back scans (points, slots)
+//   k_point_gen     1 thread / slot        segment tiles, smem binary search, coalesced slot writes
+//   k_path_walk     1 thread / path        sequential f32 chains (merge filter, advancement)
+//   k_count_scan    1 thread / slot        vertex+triangle counts, fused decoupled-look-back scan
+//   k_emit          1 thread / slot        StrokeVertexGpu (2 x 16 B stores per vertex) + u32 indices
+//   k_path_ranges   1 thread / path        per-path output ranges
+//   k_flat_count / k_flat_emit             standalone curve batches (lyon_geom flattening)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/lyon_cuda.h"
+#include "stroke_core.cuh"
+
+using namespace lyc;
+
+static_assert(sizeof(GpuVertex) == 32 && sizeof(lyon_stroke_vertex) == 32, "StrokeVertexGpu must be 32 bytes");
+
+namespace {
+
+constexpr int BLOCK = 256;
+constexpr int WARPS = BLOCK / 32;
+
+// ---------------------------------------------------------------------------------------------------------
+// Decoupled look-back (single pass chained scan).  Descriptor word: [63:62] status, [61:0] value.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint64_t ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, VAL_MASK = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Called by all 32 lanes of ONE warp. Publishes `aggregate` for `tile`, returns the exclusive prefix.
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t tile, uint64_t aggregate) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0u) {
+        if (lane == 0u) st_desc(&desc[0], ST_PREFIX | aggregate);
+        return 0ull;
+    }
+    if (lane == 0u) st_desc(&desc[tile], ST_AGG | aggregate);
+    uint64_t excl = 0ull;
+    int64_t look = (int64_t)tile - 1;
+    for (;;) {
+        int64_t idx = look - (int64_t)lane;
+        uint64_t d = ST_PREFIX;  // tiles before the first one: prefix 0
+        if (idx >= 0) {
+            do {
+                d = ld_desc(&desc[idx]);
+            } while ((d >> 62) == 0ull);
+        }
+        unsigned pmask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+        uint64_t val = d & VAL_MASK;
+        if (pmask) {
+            unsigned first = (unsigned)__ffs((int)pmask) - 1u;
+            excl += warp_sum_u64(lane <= first ? val : 0ull);
+            break;
+        }
+        excl += warp_sum_u64(val);
+        look -= 32;
+    }
+    if (lane == 0u) st_desc(&desc[tile], ST_PREFIX | (excl + aggregate));
+    return excl;
+}
+// Block-wide exclusive scan of one u32 per thread. Returns the thread's exclusive prefix; *total = block sum.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s_warp /*[WARPS+1]*/, uint32_t* total) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += y;
+    }
+    if (lane == 31u) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0u) {
+        uint32_t w = lane < (unsigned)WARPS ? s_warp[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < WARPS; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o) winc += y;
+        }
+        if (lane < (unsigned)WARPS) s_warp[lane] = winc - w;
+        if (lane == (unsigned)WARPS - 1u) s_warp[WARPS] = winc;
+    }
+    __syncthreads();
+    uint32_t r = s_warp[wid] + inc - x;
+    *total = s_warp[WARPS];
+    __syncthreads();
+    return r;
+}
+
+struct Totals {
+    unsigned long long points, slots, vertices, triangles, flat_points;
+    unsigned int error;
+    unsigned int _pad;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: per verb -- stored-point offset (scan #1), then slot count from the Wang formula (scan #2).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_seg_setup(Views w, StrokeParams p, uint32_t* ticket, uint64_t* desc_pts,
+                                                     uint64_t* desc_slots, Totals* totals) {
+    __shared__ uint32_t s_warp[WARPS + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t v = tile * BLOCK + threadIdx.x;
+    const bool valid = v < w.n_verbs;
+    const uint8_t verb = valid ? w.verbs[v] : (uint8_t)VERB_END;
+    const uint32_t npts = valid ? verb_point_count(verb, p.attr_stride) : 0u;
+    uint32_t agg;
+    uint32_t local = block_exclusive_scan(npts, s_warp, &agg);
+    if (threadIdx.x < 32) {
+        uint64_t e = lookback_exclusive(desc_pts, tile, agg);
+        if (threadIdx.x == 0) s_base = e;
+    }
+    __syncthreads();
+    const unsigned long long pt64 = s_base + local;
+    const uint32_t pt = (uint32_t)pt64;
+    float tsplit = -1.0f;
+    uint32_t nslots = 0u;
+    if (valid) {
+        nslots = seg_slot_count(verb, w.points, pt, p.attr_stride, p.tolerance, &tsplit);
+        w.seg_pt[v] = pt;
+        w.seg_tsplit[v] = tsplit;
+    }
+    __syncthreads();
+    local = block_exclusive_scan(nslots, s_warp, &agg);
+    // A single verb can ask for up to 2^32-1 slots; sum in 64 bits so the host can reject the batch.
+    unsigned long long agg64 = agg;
+    {
+        // detect u32 wrap inside the block scan: recompute the block sum in 64 bits (rare, cheap)
+        unsigned long long x = nslots;
+        x = warp_sum_u64(x);
+        __shared__ unsigned long long s_sum[WARPS];
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int i = 0; i < WARPS; ++i) t += s_sum[i];
+            s_sum[0] = t;
+        }
+        __syncthreads();
+        agg64 = s_sum[0];
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        uint64_t e = lookback_exclusive(desc_slots, tile, agg64);
+        if (threadIdx.x == 0) s_base = e;
+    }
+    __syncthreads();
+    const unsigned long long so = s_base + local;
+    if (valid) w.seg_off[v] = (uint32_t)so;
+    if (v == w.n_verbs - 1u) {
+        w.seg_pt[w.n_verbs] = (uint32_t)(pt64 + npts);
+        w.seg_off[w.n_verbs] = (uint32_t)(s_base + agg64);
+        totals->points = pt64 + npts;
+        totals->slots = s_base + agg64;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: per slot.  A block owns a tile of BLOCK verbs and walks their slots BLOCK at a time, so global
+// writes are slot-contiguous (coalesced) whatever the per-curve flatten counts are.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_point_gen(Views w, StrokeParams p) {
+    __shared__ uint32_t s_off[BLOCK + 1];
+    const uint32_t v0 = blockIdx.x * BLOCK;
+    const uint32_t nv = min((uint32_t)BLOCK, w.n_verbs - v0);
+    for (uint32_t i = threadIdx.x; i <= nv; i += BLOCK) s_off[i] = w.seg_off[v0 + i];
+    __syncthreads();
+    const uint32_t base = s_off[0];
+    const uint32_t total = s_off[nv] - base;
+    for (uint32_t i = threadIdx.x; i < total; i += BLOCK) {
+        const uint32_t s = base + i;
+        uint32_t lo = 0, hi = nv;  // last j in [0, nv) with s_off[j] <= s
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= s) lo = mid; else hi = mid;
+        }
+        point_gen_slot(w, p, v0 + lo, s, s - s_off[lo]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: per path sequential walk.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_path_walk(Views w, StrokeParams p, const uint32_t* __restrict__ path_verb_begin,
+                                                   uint32_t n_paths) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n_paths) return;
+    path_walk(w, p, path_verb_begin[path], path_verb_begin[path + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: counts + fused scan -> voff / toff (exclusive, u32; totals in 64 bits).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_count_scan(Views w, StrokeParams p, uint32_t* ticket, uint64_t* desc_v,
+                                                      uint64_t* desc_t, Totals* totals) {
+    __shared__ uint32_t s_warp[WARPS + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base_v, s_base_t;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t s = tile * BLOCK + threadIdx.x;
+    CountSink sink;
+    sink.nv = sink.nt = 0u;
+    sink.base = 0u;
+    if (s < w.n_slots) stroke_slot(w, p, s, 0u, sink);
+    uint32_t agg_v, agg_t;
+    const uint32_t lv = block_exclusive_scan(sink.nv, s_warp, &agg_v);
+    const uint32_t lt = block_exclusive_scan(sink.nt, s_warp, &agg_t);
+    if (threadIdx.x < 32) {
+        uint64_t ev = lookback_exclusive(desc_v, tile, agg_v);
+        uint64_t et = lookback_exclusive(desc_t, tile, agg_t);
+        if (threadIdx.x == 0) {
+            s_base_v = ev;
+            s_base_t = et;
+        }
+    }
+    __syncthreads();
+    if (s < w.n_slots) {
+        w.voff[s] = (uint32_t)(s_base_v + lv);
+        w.toff[s] = (uint32_t)(s_base_t + lt);
+    }
+    if (s == w.n_slots - 1u) {
+        const unsigned long long tv = s_base_v + lv + sink.nv, tt = s_base_t + lt + sink.nt;
+        w.voff[w.n_slots] = (uint32_t)tv;
+        w.toff[w.n_slots] = (uint32_t)tt;
+        totals->vertices = tv;
+        totals->triangles = tt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: emit.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_emit(Views w, StrokeParams p, GpuVertex* __restrict__ vertices,
+                                                uint32_t* __restrict__ indices, uint32_t vertex_base, Totals* totals) {
+    const uint32_t s = blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= w.n_slots) return;
+    const uint32_t vo = w.voff[s], to = w.toff[s];
+    const uint32_t nv = w.voff[s + 1] - vo, nt = w.toff[s + 1] - to;
+    if ((nv | nt) == 0u) return;
+    EmitSink sink;
+    sink.vtx = vertices + vo;
+    sink.idx = indices + 3ull * to;
+    sink.nv = sink.nt = 0u;
+    sink.base = vertex_base + vo;
+    stroke_slot(w, p, s, vertex_base, sink);
+    if (sink.nv != nv || sink.nt != nt) atomicOr(&totals->error, 1u);  // plan/emit divergence: never expected
+}
+
+__global__ void __launch_bounds__(128) k_path_ranges(Views w, const uint32_t* __restrict__ path_verb_begin, uint32_t n_paths,
+                                                     unsigned long long* path_vertex_end, unsigned long long* path_index_end,
+                                                     const Totals* totals) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n_paths) return;
+    // first slot after the path; offsets are u32-wrapped, rebuild 64-bit values monotonically is not needed:
+    // totals are checked < 2^32 for vertices; triangles likewise (see plan()).
+    const uint32_t s_end = w.seg_off[path_verb_begin[path + 1]];
+    if (path_vertex_end) path_vertex_end[path] = w.voff[s_end];
+    if (path_index_end) path_index_end[path] = 3ull * w.toff[s_end];
+    (void)totals;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Standalone curve batches: CubicBezierSegment / QuadraticBezierSegment ::for_each_flattened.
+// ---------------------------------------------------------------------------------------------------------
+template <int NPTS>  // 4 = cubic, 3 = quadratic
+__device__ __forceinline__ uint32_t curve_count(const float* __restrict__ c, float tol) {
+    if (NPTS == 4)
+        return to_u32_or_1(cubic_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol));
+    return to_u32_or_1(quad_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol));
+}
+template <int NPTS>
+__global__ void __launch_bounds__(BLOCK) k_flat_count(const float* __restrict__ ctrl, unsigned long long n, float tol,
+                                                      unsigned long long* __restrict__ offsets, uint32_t* ticket,
+                                                      uint64_t* desc, Totals* totals) {
+    __shared__ uint32_t s_warp[WARPS + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const unsigned long long i = (unsigned long long)tile * BLOCK + threadIdx.x;
+    uint32_t cnt = 0u;
+    if (i < n) {
+        float c[2 * NPTS];
+        const float2* src = reinterpret_cast<const float2*>(ctrl) + i * NPTS;
+#pragma unroll
+        for (int k = 0; k < NPTS; ++k) {
+            float2 q = src[k];
+            c[2 * k] = q.x;
+            c[2 * k + 1] = q.y;
+        }
+        cnt = curve_count<NPTS>(c, tol);
+    }
+    // counts are < 2^32 each; a block of 256 may exceed u32 only for absurd inputs -> 64-bit aggregate
+    unsigned long long x = warp_sum_u64(cnt);
+    __shared__ unsigned long long s_sum[WARPS];
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = x;
+    uint32_t agg32;
+    uint32_t local = block_exclusive_scan(cnt, s_warp, &agg32);
+    unsigned long long agg = 0;
+    for (int k = 0; k < WARPS; ++k) agg += s_sum[k];
+    if (threadIdx.x < 32) {
+        uint64_t e = lookback_exclusive(desc, tile, agg);
+        if (threadIdx.x == 0) s_base = e;
+    }
+    __syncthreads();
+    if (i < n) offsets[i] = s_base + local;
+    if (i == n - 1ull) {
+        offsets[n] = s_base + local + cnt;
+        totals->flat_points = s_base + local + cnt;
+    }
+}
+template <int NPTS>
+__global__ void __launch_bounds__(BLOCK) k_flat_emit(const float* __restrict__ ctrl, unsigned long long n, float tol,
+                                                     const unsigned long long* __restrict__ offsets,
+                                                     float2* __restrict__ out, float* __restrict__ t_out) {
+    __shared__ unsigned long long s_off[BLOCK + 1];
+    __shared__ float s_ctrl[BLOCK * 2 * NPTS];
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * BLOCK;
+    const uint32_t nc = (uint32_t)min((unsigned long long)BLOCK, n - c0);
+    for (uint32_t i = threadIdx.x; i <= nc; i += BLOCK) s_off[i] = offsets[c0 + i];
+    for (uint32_t i = threadIdx.x; i < nc * 2u * NPTS; i += BLOCK) s_ctrl[i] = ctrl[c0 * 2ull * NPTS + i];
+    __syncthreads();
+    const unsigned long long base = s_off[0];
+    const unsigned long long total = s_off[nc] - base;
+    for (unsigned long long i = threadIdx.x; i < total; i += BLOCK) {
+        const unsigned long long s = base + i;
+        uint32_t lo = 0, hi = nc;
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= s) lo = mid; else hi = mid;
+        }
+        const float* c = s_ctrl + lo * 2u * NPTS;
+        const uint32_t k = (uint32_t)(s - s_off[lo]);
+        V2 pos, prev;
+        float t;
+        if (NPTS == 4)
+            cubic_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol, k, &pos, &prev, &t);
+        else
+            quad_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol, k, &pos, &prev, &t);
+        out[s] = make_float2(pos.x, pos.y);
+        if (t_out) t_out[s] = t;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// Context / workspace
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct lyon_cuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    // workspace
+    DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, desc, misc;
+    Totals* h_totals = nullptr;  // pinned
+    // state of the last plan
+    bool planned = false;
+    Views views{};
+    StrokeParams params{};
+    const uint32_t* d_path_verb_begin = nullptr;
+    uint32_t n_paths = 0;
+    uint64_t n_vertices = 0, n_triangles = 0;
+    size_t ws_bytes = 0;
+};
+
+namespace {
+
+#define CU_TRY(ctx, expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);               \
+            return _e == cudaErrorMemoryAllocation ? LYON_ERR_OUT_OF_MEMORY : LYON_ERR_CUDA; \
+        }                                                                                  \
+    } while (0)
+
+int ensure(lyon_cuda_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return LYON_OK;
+    if (b.p) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, cudaFree(b.p));
+        c->ws_bytes -= b.cap;
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // grow-only with a little slack
+    CU_TRY(c, cudaMalloc(&b.p, want));
+    b.cap = want;
+    c->ws_bytes += want;
+    return LYON_OK;
+}
+#define TRY(expr)                  \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != LYON_OK) return _s; \
+    } while (0)
+
+inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// misc buffer layout: [0] Totals, [256..] tickets (4 x u32)
+Totals* d_totals(lyon_cuda_ctx* c) { return reinterpret_cast<Totals*>(c->misc.p); }
+uint32_t* d_ticket(lyon_cuda_ctx* c, int i) { return reinterpret_cast<uint32_t*>(static_cast<char*>(c->misc.p) + 256) + i; }
+
+int fetch_totals(lyon_cuda_ctx* c) {
+    CU_TRY(c, cudaMemcpyAsync(c->h_totals, d_totals(c), sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LYON_OK;
+}
+
+StrokeParams make_params(const lyon_stroke_options& o, uint32_t num_attributes) {
+    StrokeParams p{};
+    p.start_cap = o.start_cap;
+    p.end_cap = o.end_cap;
+    p.line_join = o.line_join;
+    p.line_width = o.line_width;
+    p.half_width = o.line_width * 0.5f;
+    p.miter_limit = o.miter_limit;
+    p.tolerance = o.tolerance;
+    // stroke.rs:603-605
+    p.merge_thr = fmaxf(fminf(o.tolerance * o.tolerance * 0.5f, o.line_width * o.line_width * 0.05f), 1e-8f);
+    p.flag_thr = p.merge_thr * 5.0f;
+    p.num_attributes = num_attributes;
+    p.attr_stride = (num_attributes + 1u) / 2u;
+    p.vw_attr = num_attributes > 0 ? o.variable_line_width : -1;  // tessellate() forces it off, stroke.rs:878
+    return p;
+}
+
+template <int NPTS>
+int flatten_count(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets, uint64_t* total) {
+    if (!c || !total || (n && (!d_ctrl || !d_offsets))) return LYON_ERR_INVALID_ARGUMENT;
+    if (!(tol > 0.0f)) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN / non-positive
+    *total = 0;
+    if (n == 0) {
+        if (d_offsets) CU_TRY(c, cudaMemsetAsync(d_offsets, 0, 8, c->stream));
+        return LYON_OK;
+    }
+    const unsigned tiles = grid_for(n, BLOCK);
+    TRY(ensure(c, c->misc, 512));
+    TRY(ensure(c, c->desc, (size_t)tiles * 8));
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 8, c->stream));
+    k_flat_count<NPTS><<<tiles, BLOCK, 0, c->stream>>>(d_ctrl, n, tol, (unsigned long long*)d_offsets, d_ticket(c, 0),
+                                                      (uint64_t*)c->desc.p, d_totals(c));
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    TRY(fetch_totals(c));
+    *total = c->h_totals->flat_points;
+    return LYON_OK;
+}
+template <int NPTS>
+int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, const uint64_t* d_offsets, uint64_t total,
+                 float* d_points, float* d_t) {
+    if (!c || (n && (!d_ctrl || !d_offsets)) || (total && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
+    if (n == 0 || total == 0) return LYON_OK;
+    k_flat_emit<NPTS><<<grid_for(n, BLOCK), BLOCK, 0, c->stream>>>(d_ctrl, n, tol, (const unsigned long long*)d_offsets,
+                                                                  (float2*)d_points, d_t);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
+    if (!out) return LYON_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LYON_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return LYON_ERR_CUDA;
+    lyon_cuda_ctx* c = new lyon_cuda_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return LYON_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    if (cudaMallocHost((void**)&c->h_totals, sizeof(Totals)) != cudaSuccess) {
+        delete c;
+        return LYON_ERR_CUDA;
+    }
+    *out = c;
+    return LYON_OK;
+}
+
+void lyon_cuda_destroy(lyon_cuda_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
+                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->desc, &c->misc};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int lyon_cuda_set_stream(lyon_cuda_ctx* c, void* stream) {
+    if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->own_stream = false;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return LYON_OK;
+}
+int lyon_cuda_synchronize(lyon_cuda_ctx* c) {
+    if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LYON_OK;
+}
+const char* lyon_cuda_last_error(const lyon_cuda_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t lyon_cuda_launch_count(const lyon_cuda_ctx* c) { return c ? c->launches : 0; }
+uint64_t lyon_cuda_workspace_bytes(const lyon_cuda_ctx* c) { return c ? c->ws_bytes : 0; }
+
+int lyon_cuda_flatten_cubics_count(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
+                                   uint64_t* total) {
+    return flatten_count<4>(c, d_ctrl, n, tol, d_offsets, total);
+}
+int lyon_cuda_flatten_cubics_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, const uint64_t* d_offsets,
+                                  uint64_t total, float* d_points, float* d_t) {
+    return flatten_emit<4>(c, d_ctrl, n, tol, d_offsets, total, d_points, d_t);
+}
+int lyon_cuda_flatten_quadratics_count(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
+                                       uint64_t* total) {
+    return flatten_count<3>(c, d_ctrl, n, tol, d_offsets, total);
+}
+int lyon_cuda_flatten_quadratics_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol,
+                                      const uint64_t* d_offsets, uint64_t total, float* d_points, float* d_t) {
+    return flatten_emit<3>(c, d_ctrl, n, tol, d_offsets, total, d_points, d_t);
+}
+
+int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t* n_vertices,
+                          uint64_t* n_indices) {
+    if (!c || !b || !o || !n_vertices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
+    *n_vertices = *n_indices = 0;
+    c->planned = false;
+    if (o->tolerance != o->tolerance) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN
+    if (o->start_cap > 2 || o->end_cap > 2 || o->line_join > 3) return LYON_ERR_INVALID_ARGUMENT;
+    if (o->variable_line_width >= 0 && b->num_attributes > 0) {
+        c->err = "variable_line_width is not implemented on the device yet";
+        return LYON_ERR_UNSUPPORTED_PARAMETER;
+    }
+    if (b->n_verbs >= SEG_MASK) return LYON_ERR_INVALID_ARGUMENT;
+    c->n_paths = b->n_paths;
+    c->n_vertices = c->n_triangles = 0;
+    c->d_path_verb_begin = b->path_verb_begin;
+    c->params = make_params(*o, b->num_attributes);
+    Views& w = c->views;
+    w = Views{};
+    w.n_verbs = b->n_verbs;
+    if (b->n_verbs == 0 || b->n_paths == 0) {
+        c->planned = true;
+        return LYON_OK;
+    }
+    if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
+    const size_t nv1 = (size_t)b->n_verbs + 1;
+    TRY(ensure(c, c->seg_pt, nv1 * 4));
+    TRY(ensure(c, c->seg_off, nv1 * 4));
+    TRY(ensure(c, c->seg_tsplit, nv1 * 4));
+    TRY(ensure(c, c->seg_id, nv1 * 4));
+    TRY(ensure(c, c->misc, 512));
+    const unsigned vtiles = grid_for(b->n_verbs, BLOCK);
+    TRY(ensure(c, c->desc, (size_t)vtiles * 16));
+    w.verbs = b->verbs;
+    w.points = reinterpret_cast<const V2*>(b->points);
+    w.seg_pt = (uint32_t*)c->seg_pt.p;
+    w.seg_off = (uint32_t*)c->seg_off.p;
+    w.seg_tsplit = (float*)c->seg_tsplit.p;
+    w.seg_id = (uint32_t*)c->seg_id.p;
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)vtiles * 16, c->stream));
+    k_seg_setup<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params, d_ticket(c, 0), (uint64_t*)c->desc.p,
+                                                (uint64_t*)c->desc.p + vtiles, d_totals(c));
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    TRY(fetch_totals(c));
+    const uint64_t n_slots = c->h_totals->slots;
+    if (c->h_totals->points > b->n_points) {
+        c->err = "verbs consume more points than the batch holds";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    if (n_slots >= 0xFFFFFFF0ull) return LYON_ERR_TOO_MANY_VERTICES;  // flatten-count explosion past u32 ids
+    w.n_slots = (uint32_t)n_slots;
+    const size_t ns1 = (size_t)n_slots + 1;
+    TRY(ensure(c, c->pos, ns1 * 8));
+    TRY(ensure(c, c->t, ns1 * 4));
+    TRY(ensure(c, c->segfs, ns1 * 4));
+    TRY(ensure(c, c->len, ns1 * 4));
+    TRY(ensure(c, c->adv, ns1 * 4));
+    TRY(ensure(c, c->voff, ns1 * 4));
+    TRY(ensure(c, c->toff, ns1 * 4));
+    const unsigned stiles = grid_for(n_slots, BLOCK);
+    TRY(ensure(c, c->desc, (size_t)stiles * 16));
+    w.pos = (V2*)c->pos.p;
+    w.t = (float*)c->t.p;
+    w.segfs = (uint32_t*)c->segfs.p;
+    w.len = (float*)c->len.p;
+    w.adv = (float*)c->adv.p;
+    w.voff = (uint32_t*)c->voff.p;
+    w.toff = (uint32_t*)c->toff.p;
+    k_point_gen<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params);
+    k_path_walk<<<grid_for(b->n_paths, 128), 128, 0, c->stream>>>(w, c->params, b->path_verb_begin, b->n_paths);
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)stiles * 16, c->stream));
+    k_count_scan<<<stiles, BLOCK, 0, c->stream>>>(w, c->params, d_ticket(c, 1), (uint64_t*)c->desc.p,
+                                                 (uint64_t*)c->desc.p + stiles, d_totals(c));
+    c->launches += 3;
+    CU_TRY(c, cudaGetLastError());
+    TRY(fetch_totals(c));
+    c->n_vertices = c->h_totals->vertices;
+    c->n_triangles = c->h_totals->triangles;
+    if (c->n_vertices > 0xFFFFFFFFull || c->n_triangles > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+    *n_vertices = c->n_vertices;
+    *n_indices = 3ull * c->n_triangles;
+    c->planned = true;
+    return LYON_OK;
+}
+
+int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint32_t* d_indices, uint64_t vertex_base,
+                          uint64_t* d_path_vertex_end, uint64_t* d_path_index_end) {
+    if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    if (!c->planned) {
+        c->err = "lyon_cuda_stroke_emit without a successful lyon_cuda_stroke_plan";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    // ids handed out are vertex_base .. vertex_base + V - 1 and must be <= u32::MAX - 1 (geometry_builder.rs:342-346)
+    if (c->n_vertices && vertex_base + c->n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (c->views.n_slots == 0 || c->views.n_verbs == 0) {
+        if (c->n_paths) {
+            if (d_path_vertex_end) CU_TRY(c, cudaMemsetAsync(d_path_vertex_end, 0, 8ull * c->n_paths, c->stream));
+            if (d_path_index_end) CU_TRY(c, cudaMemsetAsync(d_path_index_end, 0, 8ull * c->n_paths, c->stream));
+        }
+        return LYON_OK;
+    }
+    if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+    k_emit<<<grid_for(c->views.n_slots, BLOCK), BLOCK, 0, c->stream>>>(c->views, c->params, (GpuVertex*)d_vertices, d_indices,
+                                                                      (uint32_t)vertex_base, d_totals(c));
+    c->launches++;
+    if (d_path_vertex_end || d_path_index_end) {
+        k_path_ranges<<<grid_for(c->n_paths, 128), 128, 0, c->stream>>>(c->views, c->d_path_verb_begin, c->n_paths,
+                                                                       (unsigned long long*)d_path_vertex_end,
+                                                                       (unsigned long long*)d_path_index_end, d_totals(c));
+        c->launches++;
+    }
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
+// Reads back the device-side consistency flag of the last emit (plan/emit divergence => LYON_ERR_INTERNAL).
+int lyon_cuda_check(lyon_cuda_ctx* c) {
+    if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    if (!c->misc.p) return LYON_OK;
+    TRY(fetch_totals(c));
+    if (c->h_totals->error) {
+        c->err = "internal: emit pass diverged from the count pass";
+        return LYON_ERR_INTERNAL;
+    }
+    return LYON_OK;
+}
+
+int lyon_cuda_tessellate_paths(lyon_cuda_ctx* c, const lyon_path_batch* hb, const lyon_stroke_options* o,
+                               lyon_stroke_vertex** h_vertices, uint64_t* n_vertices, uint32_t** h_indices,
+                               uint64_t* n_indices) {
+    if (!c || !hb || !o || !h_vertices || !n_vertices || !h_indices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
+    *h_vertices = nullptr;
+    *h_indices = nullptr;
+    *n_vertices = *n_indices = 0;
+    if (hb->n_paths == 0 || hb->n_verbs == 0) return LYON_OK;
+    const size_t a_verbs = ((size_t)hb->n_verbs + 255) & ~(size_t)255;
+    const size_t b_points = (size_t)hb->n_points * 8;
+    const size_t b_ranges = ((size_t)hb->n_paths + 1) * 4;
+    char* d_in = nullptr;
+    CU_TRY(c, cudaMalloc((void**)&d_in, a_verbs + b_points + 256 + b_ranges));
+    lyon_path_batch db = *hb;
+    db.verbs = (const uint8_t*)d_in;
+    db.points = (const float*)(d_in + a_verbs);
+    db.path_verb_begin = (const uint32_t*)(d_in + a_verbs + ((b_points + 255) & ~(size_t)255));
+    db.path_point_begin = nullptr;
+    int st = LYON_OK;
+    void *dv = nullptr, *di = nullptr;
+    do {
+        if (cudaMemcpyAsync((void*)db.verbs, hb->verbs, hb->n_verbs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync((void*)db.points, hb->points, b_points, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync((void*)db.path_verb_begin, hb->path_verb_begin, b_ranges, cudaMemcpyHostToDevice, c->stream) !=
+                cudaSuccess) {
+            st = LYON_ERR_CUDA;
+            break;
+        }
+        uint64_t nv = 0, ni = 0;
+        st = lyon_cuda_stroke_plan(c, &db, o, &nv, &ni);
+        if (st != LYON_OK) break;
+        if (nv == 0) break;
+        if (cudaMalloc(&dv, nv * 32) != cudaSuccess || cudaMalloc(&di, (ni ? ni : 1) * 4) != cudaSuccess) {
+            st = LYON_ERR_OUT_OF_MEMORY;
+            break;
+        }
+        st = lyon_cuda_stroke_emit(c, (lyon_stroke_vertex*)dv, (uint32_t*)di, 0, nullptr, nullptr);
+        if (st != LYON_OK) break;
+        *h_vertices = (lyon_stroke_vertex*)malloc(nv * 32);
+        *h_indices = (uint32_t*)malloc((ni ? ni : 1) * 4);
+        if (!*h_vertices || !*h_indices) {
+            st = LYON_ERR_OUT_OF_MEMORY;
+            break;
+        }
+        if (cudaMemcpyAsync(*h_vertices, dv, nv * 32, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(*h_indices, di, ni * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            st = LYON_ERR_CUDA;
+            break;
+        }
+        st = lyon_cuda_check(c);
+        if (st != LYON_OK) break;
+        *n_vertices = nv;
+        *n_indices = ni;
+    } while (0);
+    cudaStreamSynchronize(c->stream);
+    if (dv) cudaFree(dv);
+    if (di) cudaFree(di);
+    cudaFree(d_in);
+    c->planned = false;  // the device batch is gone
+    if (st != LYON_OK) {
+        free(*h_vertices);
+        free(*h_indices);
+        *h_vertices = nullptr;
+        *h_indices = nullptr;
+        *n_vertices = *n_indices = 0;
+    }
+    return st;
+}
+void lyon_cuda_free_host(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,916 @@
+// stroke_core.cuh -- per-item logic of the batched stroke tessellator (host+device).
+//
+// The GPU formulation of lyon's streaming StrokeTessellator (crates/tessellation/src/stroke.rs):
+//
+//   verbs ──K1 seg_setup──▶ per-verb point offset + number of FED SLOTS (Wang counts)   [scan]
+//   slots ──K2 point_gen──▶ per-slot position / t / edge length / "maybe too close" flag
+//   paths ──K3 path_walk──▶ sequential-in-path f32 chains: merge filter, advancement, sub-path records
+//   slots ──K4 count──────▶ vertices / triangles owned by each slot                       [scan]
+//   slots ──K5 emit───────▶ StrokeVertexGpu[] and u32 indices
+//
+// A SLOT is one call of `fixed_width_step` (stroke.rs:1635) -- a Begin point, a line endpoint, one
+// flattened curve point -- or one `end()` (stroke.rs:1179).  Vertex ids are handed out in the exact
+// order of the reference's add_stroke_vertex calls: the join at kept point i is owned by slot i, and
+// everything `end()` emits (last/first edge + caps, or the closing joins) is owned by the End slot.
+//
+// Everything here is `LYC_HD` so tests/emul can run the very same code on the CPU.
+#pragma once
+#include "device_math.cuh"
+
+namespace lyc {
+
+enum : uint8_t { VERB_LINE = 0, VERB_QUAD = 1, VERB_CUBIC = 2, VERB_BEGIN = 3, VERB_CLOSE = 4, VERB_END = 5 };
+enum : uint8_t { CAP_BUTT = 0, CAP_SQUARE = 1, CAP_ROUND = 2 };
+enum : uint8_t { JOIN_MITER = 0, JOIN_MITER_CLIP = 1, JOIN_ROUND = 2, JOIN_BEVEL = 3 };
+
+static const uint32_t SEG_FS_BIT = 0x80000000u;     // slot is a flattening step (stroke.rs:1044)
+static const uint32_t SEG_END_BIT = 0x40000000u;    // slot belongs to an End/Close verb
+static const uint32_t SEG_BEGIN_BIT = 0x20000000u;  // slot belongs to a Begin verb
+static const uint32_t SEG_MASK = 0x1FFFFFFFu;
+static const uint32_t SIDE_NEG_BIT = 0x80000000u;
+static const int SIDE_POSITIVE = 0;
+static const int SIDE_NEGATIVE = 1;
+static const uint32_t MAX_ARC_SUBDIVISIONS = 20;  // reference recursion is unbounded; 2^20 vertices per arc is our cap
+
+struct StrokeParams {
+    uint8_t start_cap, end_cap, line_join, _pad;
+    float line_width, half_width, miter_limit, tolerance;
+    float merge_thr;  // square_merge_threshold (stroke.rs:603-605)
+    float flag_thr;   // 5 * merge_thr: conservative pre-filter, see point_gen
+    uint32_t num_attributes, attr_stride;
+    int32_t vw_attr;
+};
+
+struct GpuVertex {  // == lyon_stroke_vertex
+    float px, py, nx, ny, advancement, half_width;
+    uint32_t src;
+    float t;
+};
+
+struct Views {
+    const uint8_t* verbs;
+    const V2* points;
+    uint32_t n_verbs;
+    // per verb (n_verbs + 1)
+    uint32_t* seg_pt;    // index of the verb's first stored point
+    uint32_t* seg_off;   // first slot of the verb
+    float* seg_tsplit;   // quadratic sharp-turn split parameter, or -1
+    uint32_t* seg_id;    // EndpointId of the verb's endpoint (written by path_walk)
+    // per slot
+    V2* pos;
+    float* t;
+    uint32_t* segfs;
+    float* len;   // |P_s - P_{s-1}|; sign bit set when the pair MAY be within the merge threshold
+    float* adv;   // advancement; NaN = point dropped by the merge filter
+    uint32_t* voff;
+    uint32_t* toff;
+    uint32_t n_slots;
+};
+
+LYC_HD uint32_t verb_point_count(uint8_t verb, uint32_t a) {
+    switch (verb) {
+        case VERB_BEGIN:
+        case VERB_LINE:
+        case VERB_CLOSE: return 1u + a;
+        case VERB_QUAD: return 2u + a;
+        case VERB_CUBIC: return 3u + a;
+        default: return 0u;
+    }
+}
+LYC_HD V2 seg_from_point(const V2* points, uint32_t pt, uint32_t a) {
+    uint32_t back = 1u + a;
+    return points[pt >= back ? pt - back : 0u];
+}
+
+// K1: number of slots of verb v (Wang counts of cubic_bezier.rs:590-603 / quadratic_bezier.rs:368-380,
+// quads possibly split in two by flatten_quad, stroke.rs:2755-2779).
+LYC_HD uint32_t seg_slot_count(uint8_t verb, const V2* points, uint32_t pt, uint32_t a, float tol, float* tsplit_out) {
+    *tsplit_out = -1.0f;
+    if (verb == VERB_CUBIC) {
+        V2 from = seg_from_point(points, pt, a);
+        return to_u32_or_1(cubic_wang(from, points[pt], points[pt + 1], points[pt + 2], tol));
+    }
+    if (verb == VERB_QUAD) {
+        V2 from = seg_from_point(points, pt, a);
+        V2 ctrl = points[pt], to = points[pt + 1];
+        float ts;
+        if (find_sharp_turn(from, ctrl, to, &ts)) {
+            *tsplit_out = ts;
+            V2 sp = quad_sample(from, ctrl, to, ts);  // QuadraticBezierSegment::split, quadratic_bezier.rs:208-223
+            uint32_t n1 = to_u32_or_1(quad_wang(from, lerp(from, ctrl, ts), sp, tol));
+            uint32_t n2 = to_u32_or_1(quad_wang(sp, lerp(ctrl, to, ts), to, tol));
+            return n1 + n2;
+        }
+        return to_u32_or_1(quad_wang(from, ctrl, to, tol));
+    }
+    return 1u;  // Begin, Line, End, Close
+}
+
+struct SlotPoint {
+    V2 pos, prev;
+    float t;
+    bool fs, has_prev;
+};
+// One flattened point of a quadratic (the k-th callback of for_each_flattened_with_t) and its predecessor.
+LYC_HD void quad_point(V2 from, V2 ctrl, V2 to, float tol, uint32_t k, V2* pos, V2* prev, float* t_out) {
+    float n = quad_wang(from, ctrl, to, tol);
+    float step = 1.0f / n;
+    uint32_t cnt = to_u32_or_1(n);
+    QuadPoly poly = quad_poly(from, ctrl, to);
+    float tp = 0.0f, tc = 0.0f;
+    uint32_t adds = (k + 1u < cnt) ? k + 1u : k;  // the last point is the exact endpoint (t == 1.0)
+    for (uint32_t i = 0; i < adds; ++i) {
+        tp = tc;
+        tc = tc + step;
+    }
+    if (k + 1u < cnt) {
+        *pos = quad_poly_sample(poly, tc);
+        *t_out = tc;
+        *prev = (k == 0u) ? from : quad_poly_sample(poly, tp);
+    } else {
+        *pos = to;
+        *t_out = 1.0f;
+        *prev = (k == 0u) ? from : quad_poly_sample(poly, tc);
+    }
+}
+LYC_HD void cubic_point(V2 from, V2 c1, V2 c2, V2 to, float tol, uint32_t k, V2* pos, V2* prev, float* t_out) {
+    float n = cubic_wang(from, c1, c2, to, tol);
+    float step = 1.0f / n;
+    uint32_t cnt = to_u32_or_1(n);
+    CubicPoly poly = cubic_poly(from, c1, c2, to);
+    float tp = 0.0f, tc = 0.0f;
+    uint32_t adds = (k + 1u < cnt) ? k + 1u : k;
+    for (uint32_t i = 0; i < adds; ++i) {
+        tp = tc;
+        tc = tc + step;
+    }
+    if (k + 1u < cnt) {
+        *pos = cubic_poly_sample(poly, tc);
+        *t_out = tc;
+        *prev = (k == 0u) ? from : cubic_poly_sample(poly, tp);
+    } else {
+        *pos = to;
+        *t_out = 1.0f;
+        *prev = (k == 0u) ? from : cubic_poly_sample(poly, tc);
+    }
+}
+
+// K2: evaluate slot k of verb v.
+LYC_HD SlotPoint eval_slot(uint8_t verb, const V2* points, uint32_t pt, uint32_t a, float tol, float tsplit, uint32_t k) {
+    SlotPoint r;
+    r.t = 1.0f;
+    r.fs = false;
+    r.has_prev = true;
+    r.prev = v2(0.0f, 0.0f);
+    switch (verb) {
+        case VERB_BEGIN:
+            r.pos = points[pt];
+            r.has_prev = false;
+            break;
+        case VERB_LINE:
+            r.pos = points[pt];
+            r.prev = seg_from_point(points, pt, a);
+            break;
+        case VERB_CUBIC: {
+            V2 from = seg_from_point(points, pt, a);
+            cubic_point(from, points[pt], points[pt + 1], points[pt + 2], tol, k, &r.pos, &r.prev, &r.t);
+            r.fs = r.t != 1.0f;
+            break;
+        }
+        case VERB_QUAD: {
+            V2 from = seg_from_point(points, pt, a);
+            V2 ctrl = points[pt], to = points[pt + 1];
+            if (tsplit >= 0.0f) {
+                V2 sp = quad_sample(from, ctrl, to, tsplit);
+                V2 bc = lerp(from, ctrl, tsplit);
+                V2 ac = lerp(ctrl, to, tsplit);
+                uint32_t n1 = to_u32_or_1(quad_wang(from, bc, sp, tol));
+                float ts;
+                if (k < n1) {
+                    quad_point(from, bc, sp, tol, k, &r.pos, &r.prev, &ts);
+                    r.fs = ts != 1.0f;
+                    r.t = ts * tsplit;  // stroke.rs:2764
+                } else {
+                    quad_point(sp, ac, to, tol, k - n1, &r.pos, &r.prev, &ts);
+                    r.fs = ts != 1.0f;
+                    r.t = tsplit + ts * (1.0f - tsplit);  // stroke.rs:2770
+                }
+            } else {
+                quad_point(from, ctrl, to, tol, k, &r.pos, &r.prev, &r.t);
+                r.fs = r.t != 1.0f;
+            }
+            break;
+        }
+        default:  // End / Close: not a point
+            r.pos = v2(0.0f, 0.0f);
+            r.has_prev = false;
+            break;
+    }
+    return r;
+}
+
+// K2 per slot: writes pos/t/segfs/len.  The merge filter of fixed_width_step_impl (stroke.rs:1530-1536)
+// compares against the last KEPT point, which is sequential; here we only pre-classify: a pair further
+// apart than sqrt(5)x the merge distance can never be merged whatever was dropped before it (triangle
+// inequality with margin), so path_walk only has to look at the flagged pairs.
+LYC_HD void point_gen_slot(const Views& w, const StrokeParams& p, uint32_t v, uint32_t s, uint32_t k) {
+    uint8_t verb = w.verbs[v];
+    if (verb == VERB_END || verb == VERB_CLOSE) {
+        w.segfs[s] = v | SEG_END_BIT;
+        w.t[s] = 1.0f;
+        w.len[s] = 0.0f;
+        return;  // pos[s] / adv[s] are written by path_walk (sub-path record)
+    }
+    SlotPoint r = eval_slot(verb, w.points, w.seg_pt[v], p.attr_stride, p.tolerance, w.seg_tsplit[v], k);
+    w.pos[s] = r.pos;
+    w.t[s] = r.t;
+    w.segfs[s] = v | (r.fs ? SEG_FS_BIT : 0u) | (verb == VERB_BEGIN ? SEG_BEGIN_BIT : 0u);
+    float l = 0.0f;
+    if (r.has_prev) {
+        V2 d = r.pos - r.prev;
+        float d2 = sqlen(d);
+        l = sqrtf(d2);
+        if (!(d2 >= p.flag_thr)) l = -l;  // also flags NaN distances; -0.0f keeps the flag for zero length
+    }
+    w.len[s] = l;
+}
+LYC_HD bool len_flagged(float l) { return (l != l) || signbit(l); }
+
+// Sub-path record stored in pos[end_slot] by path_walk.
+LYC_HD uint32_t f2u(float f) {
+    union {
+        float f;
+        uint32_t u;
+    } c;
+    c.f = f;
+    return c.u;
+}
+LYC_HD float u2f(uint32_t u) {
+    union {
+        float f;
+        uint32_t u;
+    } c;
+    c.u = u;
+    return c.f;
+}
+static const uint32_t REC_MNEC = 4u, REC_CLOSE = 8u;
+
+// K3: one path, sequential.  Restates the parts of the stroker that are loop-carried in f32:
+//   * merge filter against the last kept point          (stroke.rs:1318-1320, 1530-1536)
+//   * advancement chain adv += |edge|                     (stroke.rs:1546-1550, 1657-1661, 1759-1769, 2140)
+//   * sub_path_start_advancement carry (open sub-paths only, stroke.rs:1359)
+//   * may_need_empty_cap                                   (stroke.rs:1180, 1533)
+//   * endpoint ids: sequential per event (stroke.rs:882-937) or point-array offsets (path.rs:1197-1263)
+LYC_HD void path_walk(const Views& w, const StrokeParams& p, uint32_t vb, uint32_t ve) {
+    const float nan = u2f(0x7FC00000u);
+    float carry = 0.0f, adv = 0.0f;
+    uint32_t evt = 0, begin_slot = 0, last_kept = 0, m = 0;
+    bool mnec = false;
+    const bool with_ids = p.num_attributes > 0;
+    const uint32_t pt_base = vb < ve ? w.seg_pt[vb] : 0u;
+    for (uint32_t v = vb; v < ve; ++v) {
+        uint8_t verb = w.verbs[v];
+        uint32_t s0 = w.seg_off[v], s1 = w.seg_off[v + 1];
+        if (verb == VERB_BEGIN) {
+            begin_slot = s0;
+            last_kept = s0;
+            m = 1;
+            mnec = false;
+            adv = carry;
+            w.adv[s0] = adv;
+            w.seg_id[v] = with_ids ? (w.seg_pt[v] - pt_base) : evt;
+            evt++;
+        } else if (verb == VERB_END || verb == VERB_CLOSE) {
+            bool close = verb == VERB_CLOSE;
+            if (close && m == 1) mnec = true;
+            V2 rec;
+            rec.x = u2f(begin_slot);
+            rec.y = u2f((m > 3u ? 3u : m) | (mnec ? REC_MNEC : 0u) | (close ? REC_CLOSE : 0u));
+            w.pos[s0] = rec;
+            w.adv[s0] = nan;
+            if (!(close && m > 2u) && m >= 2u) carry = adv;
+            m = 0;
+        } else {
+            uint32_t npts = verb == VERB_LINE ? 1u : (verb == VERB_QUAD ? 2u : 3u);
+            w.seg_id[v] = with_ids ? (w.seg_pt[v] + npts - 1u - pt_base) : evt;
+            evt++;
+            for (uint32_t s = s0; s < s1; ++s) {
+                float l = w.len[s];
+                if (len_flagged(l) || last_kept != s - 1u) {
+                    V2 pl = w.pos[last_kept], ps = w.pos[s];
+                    if (sqlen(pl - ps) < p.merge_thr) {
+                        w.adv[s] = nan;
+                        if (m == 1u) mnec = true;
+                        continue;
+                    }
+                    l = length(ps - pl);
+                }
+                adv = adv + l;
+                w.adv[s] = adv;
+                last_kept = s;
+                m++;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Join geometry (fixed line width)
+// ---------------------------------------------------------------------------------------------------------
+struct Join {
+    bool fast;
+    bool fold[2];
+    bool has_single[2];
+    uint8_t line_join;
+    V2 single[2], prev[2], next[2];
+    V2 normal;  // fast path vertex normal
+    uint32_t prev_v[2], next_v[2];
+};
+LYC_HD bool miter_limit_is_exceeded(V2 normal, float miter_limit) {  // stroke.rs:2320-2322
+    return sqlen(normal) > miter_limit * miter_limit * 4.0f;
+}
+LYC_HD float circle_flattening_step(float radius, float tolerance) {  // stroke.rs:2749-2753
+    tolerance = fminf(tolerance, radius);
+    return 2.0f * libm_acos((radius - tolerance) / radius);
+}
+LYC_HD void get_clip_intersections(V2 previous_normal, V2 next_normal, V2 normal, float clip_distance, V2* i1,
+                                   V2* i2) {  // stroke.rs:2279-2315
+    LineD clip_line = line_d(normalize(normal) * clip_distance, tangent(normal));
+    LineD prev_line = line_d(previous_normal, tangent(previous_normal));
+    LineD next_line = line_d(next_normal, tangent(next_normal));
+    if (!line_intersection(clip_line, prev_line, i1)) *i1 = normal;
+    if (!line_intersection(clip_line, next_line, i2)) *i2 = normal;
+}
+
+// fixed_width_step_impl's choice between flattened_step (stroke.rs:1743-1806) and
+// compute_join_side_positions_fixed_width (stroke.rs:1643-1733) for the join at `pj`.
+LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const StrokeParams& o) {
+    const float hw = o.half_width;
+    V2 prev_edge = pj - pp;
+    V2 next_edge = pn - pj;
+    float prev_length = length(prev_edge);
+    float next_length = length(next_edge);
+    V2 prev_tangent = prev_edge / prev_length;
+    V2 next_tangent = next_edge / next_length;
+    V2 normal = compute_normal(prev_tangent, next_tangent);
+    j.fold[0] = j.fold[1] = false;
+    j.fast = join_fs && dot(prev_edge, next_edge) > 0.0f;  // stroke.rs:1568-1574
+    j.normal = normal;
+    if (j.fast) {
+        j.line_join = JOIN_MITER;
+        V2 p0 = pj + normal * hw;
+        V2 p1 = pj - normal * hw;
+        j.prev[SIDE_POSITIVE] = j.next[SIDE_POSITIVE] = j.single[SIDE_POSITIVE] = p0;
+        j.prev[SIDE_NEGATIVE] = j.next[SIDE_NEGATIVE] = j.single[SIDE_NEGATIVE] = p1;
+        j.has_single[0] = j.has_single[1] = true;
+        return;
+    }
+    j.line_join = o.line_join;
+    j.has_single[0] = j.has_single[1] = false;
+    int front_side;
+    V2 front_normal;
+    if (cross(prev_tangent, next_tangent) >= 0.0f) {
+        front_side = SIDE_NEGATIVE;
+        front_normal = -normal;
+    } else {
+        front_side = SIDE_POSITIVE;
+        front_normal = normal;
+    }
+    int back_side = 1 - front_side;
+    V2 extruded_normal = front_normal * hw;
+    bool unclipped_miter =
+        (j.line_join == JOIN_MITER || j.line_join == JOIN_MITER_CLIP) && !miter_limit_is_exceeded(front_normal, o.miter_limit);
+    bool fold = false;
+    bool angle_is_sharp = dot(next_tangent, prev_tangent) < 0.0f;
+    if (!unclipped_miter && angle_is_sharp) {
+        float d_next = dot(extruded_normal, -next_tangent) - next_length;
+        float d_prev = dot(extruded_normal, prev_tangent) - prev_length;
+        if (fminf(d_next, d_prev) > 0.0f || sqlen(normal) < 1e-5f) {
+            j.fold[front_side] = true;
+            fold = true;
+        }
+    }
+    V2 n0 = v2(-prev_tangent.y, prev_tangent.x) * hw;
+    V2 n1 = v2(-next_tangent.y, next_tangent.x) * hw;
+    j.prev[SIDE_POSITIVE] = pj + n0;
+    j.next[SIDE_POSITIVE] = pj + n1;
+    j.prev[SIDE_NEGATIVE] = pj - n0;
+    j.next[SIDE_NEGATIVE] = pj - n1;
+    j.single[0] = j.single[1] = pj;
+    if (!fold) {
+        V2 mp = pj + normal * hw;
+        V2 mn = pj - normal * hw;
+        j.has_single[back_side] = true;
+        j.single[back_side] = back_side == SIDE_POSITIVE ? mp : mn;
+        if (unclipped_miter) {
+            j.has_single[front_side] = true;
+            j.single[front_side] = front_side == SIDE_POSITIVE ? mp : mn;
+        } else if (j.line_join == JOIN_MITER_CLIP) {
+            V2 c0 = j.prev[front_side] - pj;
+            V2 c1 = j.next[front_side] - pj;
+            V2 pn_, nn_;
+            get_clip_intersections(c0, c1, front_normal, o.miter_limit * hw, &pn_, &nn_);
+            j.prev[front_side] = pj + pn_;
+            j.next[front_side] = pj + nn_;
+        }
+    }
+}
+// Vertex ids of a join whose first vertex is `base`, in add_stroke_vertex order:
+// fast path Positive then Negative (stroke.rs:1791-1797); otherwise Negative side then Positive side,
+// each one vertex (single) or two (prev, next) (stroke.rs:1595-1608, 2024-2055).
+LYC_HD uint32_t join_assign_ids(Join& j, uint32_t base) {
+    if (j.fast) {
+        j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = base;
+        j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = base + 1u;
+        return 2u;
+    }
+    uint32_t n = 0;
+    for (int side = SIDE_NEGATIVE; side >= SIDE_POSITIVE; --side) {
+        if (j.has_single[side]) {
+            j.prev_v[side] = j.next_v[side] = base + n;
+            n += 1u;
+        } else {
+            j.prev_v[side] = base + n;
+            j.next_v[side] = base + n + 1u;
+            n += 2u;
+        }
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sinks: the count pass and the emit pass run the SAME emission code against different sinks.
+// ---------------------------------------------------------------------------------------------------------
+struct VertexTemplate {  // StrokeVertexData minus normal/side (stroke.rs:2656-2665)
+    V2 position_on_path;
+    float half_width, advancement;
+    uint32_t src;  // endpoint id
+    float t;
+};
+struct CountSink {
+    uint32_t nv, nt, base;
+    LYC_HD uint32_t next_id() const { return base + nv; }
+    LYC_HD uint32_t add_vertex(const VertexTemplate&, V2, bool) { return base + nv++; }
+    LYC_HD void add_triangle(uint32_t, uint32_t, uint32_t) { nt++; }
+    LYC_HD void bulk(uint32_t vertices, uint32_t triangles) {
+        nv += vertices;
+        nt += triangles;
+    }
+    static const bool kCounting = true;
+};
+struct EmitSink {
+    GpuVertex* vtx;  // first vertex owned by this slot
+    uint32_t* idx;   // first index owned by this slot
+    uint32_t nv, nt, base;
+    LYC_HD uint32_t next_id() const { return base + nv; }
+    LYC_HD uint32_t add_vertex(const VertexTemplate& vt, V2 normal, bool negative) {
+#ifdef __CUDA_ARCH__
+        float4* dst = reinterpret_cast<float4*>(vtx + nv);
+        dst[0] = make_float4(vt.position_on_path.x, vt.position_on_path.y, normal.x, normal.y);
+        dst[1] = make_float4(vt.advancement, vt.half_width,
+                             __uint_as_float((vt.src & 0x7FFFFFFFu) | (negative ? SIDE_NEG_BIT : 0u)), vt.t);
+#else
+        GpuVertex g;
+        g.px = vt.position_on_path.x;
+        g.py = vt.position_on_path.y;
+        g.nx = normal.x;
+        g.ny = normal.y;
+        g.advancement = vt.advancement;
+        g.half_width = vt.half_width;
+        g.src = (vt.src & 0x7FFFFFFFu) | (negative ? SIDE_NEG_BIT : 0u);
+        g.t = vt.t;
+        vtx[nv] = g;
+#endif
+        return base + nv++;
+    }
+    LYC_HD void add_triangle(uint32_t a, uint32_t b, uint32_t c) {
+        uint32_t* d = idx + 3u * (size_t)nt;
+        d[0] = a;
+        d[1] = b;
+        d[2] = c;
+        nt++;
+    }
+    LYC_HD void bulk(uint32_t, uint32_t) {}
+    static const bool kCounting = false;
+};
+
+// stroke.rs:1869-1904.  (ids of p0 after its join, ids of p1 before its join, with the fold remaps)
+template <class Sink>
+LYC_HD void add_edge_triangles(Sink& sink, const uint32_t p0_prev_v[2], const uint32_t p0_next_v[2], const bool p0_fold[2],
+                               const uint32_t p1_prev_v[2], const uint32_t p1_next_v[2], const bool p1_fold[2]) {
+    uint32_t p0_neg = p0_next_v[SIDE_NEGATIVE];
+    uint32_t p0_pos = p0_next_v[SIDE_POSITIVE];
+    uint32_t p1_neg = p1_prev_v[SIDE_NEGATIVE];
+    uint32_t p1_pos = p1_prev_v[SIDE_POSITIVE];
+    if (p0_fold[SIDE_POSITIVE]) p0_neg = p0_prev_v[SIDE_POSITIVE];
+    if (p0_fold[SIDE_NEGATIVE]) p0_pos = p0_prev_v[SIDE_NEGATIVE];
+    if (p1_fold[SIDE_POSITIVE]) p1_neg = p1_next_v[SIDE_POSITIVE];
+    if (p1_fold[SIDE_NEGATIVE]) p1_pos = p1_next_v[SIDE_NEGATIVE];
+    if (p0_neg == p1_pos) return;
+    if (p0_neg != p0_pos && p0_pos != p1_pos) sink.add_triangle(p0_neg, p0_pos, p1_pos);
+    if (p0_neg != p1_neg && p1_pos != p1_neg) sink.add_triangle(p0_neg, p1_pos, p1_neg);
+}
+template <class Sink>
+LYC_HD void add_edge_triangles(Sink& sink, const Join& a, const Join& b) {
+    add_edge_triangles(sink, a.prev_v, a.next_v, a.fold, b.prev_v, b.next_v, b.fold);
+}
+
+// tessellate_arc (stroke.rs:2612-2653): 2^k - 1 vertices in PRE-ORDER, each followed by its triangle.
+// The recursion is unrolled per node: node j re-derives its angle interval and corner ids by descending
+// from the root with the same sequence of f32 midpoints the recursion computes.
+template <class Sink>
+LYC_HD void emit_arc(Sink& sink, const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb,
+                     uint32_t k) {
+    if (k == 0u) return;
+    if (k > MAX_ARC_SUBDIVISIONS) k = MAX_ARC_SUBDIVISIONS;
+    const uint32_t total = (1u << k) - 1u;
+    if (Sink::kCounting) {
+        sink.bulk(total, total);
+        return;
+    }
+    const uint32_t first_id = sink.next_id();
+    for (uint32_t j = 0; j < total; ++j) {
+        float lo = a0, hi = a1;
+        uint32_t ida = va, idb = vb, base = 0u, size = total;
+        float mid;
+        uint32_t id;
+        for (;;) {
+            mid = (lo + hi) * 0.5f;
+            id = first_id + base;
+            if (j == base) break;
+            uint32_t half = (size - 1u) >> 1;
+            if (j <= base + half) {
+                hi = mid;
+                idb = id;
+                base += 1u;
+            } else {
+                lo = mid;
+                ida = id;
+                base += 1u + half;
+            }
+            size = half;
+        }
+        sink.add_vertex(vt, v2(libm_cos(mid), libm_sin(mid)), negative);
+        sink.add_triangle(ida, id, idb);
+    }
+}
+LYC_HD uint32_t arc_subdivisions(float diff, float radius, float tolerance) {  // stroke.rs:2002-2004, 2488-2490
+    float stp = circle_flattening_step(radius, tolerance);
+    float num_segments = ceilf(fabsf(diff) / stp);
+    return sat_u32(roundf(libm_log2(num_segments)));
+}
+
+// tessellate_round_join (stroke.rs:1968-2021)
+template <class Sink>
+LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Join& j, int side, const StrokeParams& o) {
+    V2 center = vt.position_on_path;
+    float radius = vt.half_width;
+    V2 start_normal = j.prev[side] - center;
+    V2 end_normal = j.next[side] - center;
+    uint32_t start_vertex = j.prev_v[side];
+    uint32_t end_vertex = j.next_v[side];
+    float angle_sign = side == SIDE_NEGATIVE ? 1.0f : -1.0f;
+    float start_angle = angle_from_x_axis(start_normal);
+    float diff = angle_to(start_angle, angle_from_x_axis(end_normal));
+    if (diff * angle_sign < 0.0f) diff = angle_sign * (2.0f * LYC_PI_F - fabsf(diff));
+    float end_angle = start_angle + diff;
+    if (side == SIDE_NEGATIVE) {
+        float ta = start_angle;
+        start_angle = end_angle;
+        end_angle = ta;
+        uint32_t tv = start_vertex;
+        start_vertex = end_vertex;
+        end_vertex = tv;
+    }
+    uint32_t k = arc_subdivisions(diff, radius, o.tolerance);
+    emit_arc(sink, vt, side != SIDE_POSITIVE, start_angle, end_angle, start_vertex, end_vertex, k);
+}
+
+// tessellate_join (stroke.rs:1907-1965)
+template <class Sink>
+LYC_HD void tessellate_join(Sink& sink, const VertexTemplate& vt, const Join& j, const StrokeParams& o) {
+    bool need0 = !j.has_single[SIDE_POSITIVE] && !j.fold[SIDE_NEGATIVE];
+    bool need1 = !j.has_single[SIDE_NEGATIVE] && !j.fold[SIDE_POSITIVE];
+    if (!j.fold[SIDE_POSITIVE] && !j.fold[SIDE_NEGATIVE]) {
+        if (need0 && need1) {
+            sink.add_triangle(j.prev_v[SIDE_POSITIVE], j.next_v[SIDE_POSITIVE], j.next_v[SIDE_NEGATIVE]);
+            sink.add_triangle(j.prev_v[SIDE_POSITIVE], j.next_v[SIDE_NEGATIVE], j.prev_v[SIDE_NEGATIVE]);
+        } else if (!need0 && need1) {
+            sink.add_triangle(j.prev_v[SIDE_NEGATIVE], j.prev_v[SIDE_POSITIVE], j.next_v[SIDE_NEGATIVE]);
+        } else if (need0 && !need1) {
+            sink.add_triangle(j.prev_v[SIDE_NEGATIVE], j.prev_v[SIDE_POSITIVE], j.next_v[SIDE_POSITIVE]);
+        }
+    }
+    if (j.line_join == JOIN_ROUND) {
+        if (need0) tessellate_round_join(sink, vt, j, SIDE_POSITIVE, o);
+        if (need1) tessellate_round_join(sink, vt, j, SIDE_NEGATIVE, o);
+    }
+}
+
+// Vertices of a join, in the reference's order.  Fills j.prev_v / j.next_v.
+template <class Sink>
+LYC_HD void emit_join_vertices(Sink& sink, const VertexTemplate& vt, Join& j) {
+    if (j.fast) {  // flattened_step, stroke.rs:1791-1803
+        uint32_t pv = sink.add_vertex(vt, j.normal, false);
+        uint32_t nv = sink.add_vertex(vt, -j.normal, true);
+        j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = pv;
+        j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = nv;
+        return;
+    }
+    for (int side = SIDE_NEGATIVE; side >= SIDE_POSITIVE; --side) {  // add_join_base_vertices, stroke.rs:2024-2055
+        bool neg = side == SIDE_NEGATIVE;
+        if (j.has_single[side]) {
+            uint32_t id = sink.add_vertex(vt, (j.single[side] - vt.position_on_path) / vt.half_width, neg);
+            j.prev_v[side] = j.next_v[side] = id;
+        } else {
+            j.prev_v[side] = sink.add_vertex(vt, (j.prev[side] - vt.position_on_path) / vt.half_width, neg);
+            j.next_v[side] = sink.add_vertex(vt, (j.next[side] - vt.position_on_path) / vt.half_width, neg);
+        }
+    }
+}
+
+// tessellate_round_cap (stroke.rs:2459-2524)
+template <class Sink>
+LYC_HD void tessellate_round_cap(Sink& sink, VertexTemplate vt, V2 center, float radius, V2 start_normal,
+                                 uint32_t start_vertex, uint32_t end_vertex, V2 edge_normal, bool is_start,
+                                 const StrokeParams& o) {
+    if (radius < o.tolerance) return;
+    bool first_side_positive = is_start ^ (cross(edge_normal, start_normal) >= 0.0f);
+    float start_angle = angle_from_x_axis(start_normal);
+    float diff = angle_to(start_angle, angle_from_x_axis(edge_normal));
+    float mid_angle = start_angle + diff;
+    float end_angle = mid_angle + diff;
+    uint32_t k = arc_subdivisions(diff, radius, o.tolerance);
+    vt.position_on_path = center;
+    vt.half_width = radius;
+    uint32_t mid_vertex = sink.add_vertex(vt, normalize(edge_normal), !first_side_positive);
+    sink.add_triangle(start_vertex, mid_vertex, end_vertex);
+    emit_arc(sink, vt, !first_side_positive, start_angle, mid_angle, start_vertex, mid_vertex, k);
+    emit_arc(sink, vt, first_side_positive, mid_angle, end_angle, mid_vertex, end_vertex, k);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Slot neighbourhood helpers
+// ---------------------------------------------------------------------------------------------------------
+LYC_HD bool slot_dropped(const Views& w, uint32_t s) { return is_nan(w.adv[s]); }
+LYC_HD uint32_t prev_kept(const Views& w, uint32_t s) {  // s is a kept non-Begin point: a kept predecessor exists
+    uint32_t j = s - 1u;
+    while (slot_dropped(w, j)) --j;
+    return j;
+}
+LYC_HD uint32_t next_kept_or_end(const Views& w, uint32_t s) {  // returns the End slot when s is the last kept point
+    uint32_t j = s + 1u;
+    while (!(w.segfs[j] & SEG_END_BIT) && slot_dropped(w, j)) ++j;
+    return j;
+}
+LYC_HD VertexTemplate slot_vertex_template(const Views& w, const StrokeParams& o, uint32_t s) {
+    VertexTemplate vt;
+    vt.position_on_path = w.pos[s];
+    vt.half_width = o.half_width;
+    vt.advancement = w.adv[s];
+    vt.src = w.seg_id[w.segfs[s] & SEG_MASK];
+    vt.t = w.t[s];
+    return vt;
+}
+// Join at kept interior point `s` as computed while the stream was running (not by end()).
+LYC_HD void stream_join(const Views& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, Join& j) {
+    compute_join_fw(j, w.pos[pk], w.pos[s], w.pos[nk], (w.segfs[s] & SEG_FS_BIT) != 0u, o);
+}
+// Base vertex id of slot s. Counting pass: ids are never compared across slots in a way that matters for
+// fixed width, any distinct bases do.
+template <class Sink>
+LYC_HD uint32_t slot_vertex_base(const Views& w, uint32_t s, uint32_t global_base) {
+    return Sink::kCounting ? (0x40000000u + (s & 0xFFFFFu) * 16u) : (global_base + w.voff[s]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4/K5 per slot
+// ---------------------------------------------------------------------------------------------------------
+template <class Sink>
+LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink);
+
+template <class Sink>
+LYC_HD void stroke_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink) {
+    uint32_t sf = w.segfs[s];
+    if (sf & SEG_END_BIT) {
+        stroke_end_slot(w, o, s, global_base, sink);
+        return;
+    }
+    if ((sf & SEG_BEGIN_BIT) || slot_dropped(w, s)) return;
+    uint32_t nk = next_kept_or_end(w, s);
+    if (w.segfs[nk] & SEG_END_BIT) return;  // last kept point: owned by the End slot
+    uint32_t pk = prev_kept(w, s);
+    Join j;
+    stream_join(w, o, s, pk, nk, j);
+    VertexTemplate vt = slot_vertex_template(w, o, s);
+    emit_join_vertices(sink, vt, j);
+    if (!(w.segfs[pk] & SEG_BEGIN_BIT)) {  // count > 2: edge between the previous join and this one (stroke.rs:1611-1613)
+        uint32_t pk2 = prev_kept(w, pk);
+        Join jp;
+        stream_join(w, o, pk, pk2, s, jp);
+        join_assign_ids(jp, slot_vertex_base<Sink>(w, pk, global_base));
+        add_edge_triangles(sink, jp, j);
+    }
+    tessellate_join(sink, vt, j, o);
+}
+
+// Side points of the first point of a sub-path, computed when the second kept point arrives
+// (fixed_width_step_impl count == 1, stroke.rs:1538-1556).
+LYC_HD void first_point_side_next(V2 p0, V2 p1, float hw, V2 next[2]) {
+    V2 edge = p1 - p0;
+    float len = length(edge);
+    V2 tg = edge / len;
+    V2 n = v2(-tg.y, tg.x) * hw;
+    next[SIDE_POSITIVE] = p0 + n;
+    next[SIDE_NEGATIVE] = p0 - n;
+}
+
+// tessellate_empty_square_cap / tessellate_empty_round_cap (stroke.rs:2526-2609) via tessellate_empty_cap (:1282-1316)
+template <class Sink>
+LYC_HD void tessellate_empty_cap(Sink& sink, VertexTemplate vt, const StrokeParams& o) {
+    V2 c = vt.position_on_path;
+    if (o.start_cap == CAP_SQUARE) {
+        uint32_t a = sink.add_vertex(vt, v2(1.0f, 1.0f), true);
+        uint32_t b = sink.add_vertex(vt, v2(1.0f, -1.0f), false);
+        uint32_t cc = sink.add_vertex(vt, v2(-1.0f, -1.0f), false);
+        uint32_t d = sink.add_vertex(vt, v2(-1.0f, 1.0f), true);
+        sink.add_triangle(a, b, cc);
+        sink.add_triangle(a, cc, d);
+    } else if (o.start_cap == CAP_ROUND) {
+        float radius = vt.half_width;
+        uint32_t left_id = sink.add_vertex(vt, v2(-1.0f, 0.0f), false);
+        uint32_t right_id = sink.add_vertex(vt, v2(1.0f, 0.0f), true);
+        tessellate_round_cap(sink, vt, c, radius, v2(-1.0f, 0.0f), left_id, right_id, v2(0.0f, 1.0f), true, o);
+        tessellate_round_cap(sink, vt, c, radius, v2(1.0f, 0.0f), right_id, left_id, v2(0.0f, -1.0f), false, o);
+    }
+}
+
+// Everything `end()` emits for one sub-path (stroke.rs:1179-1193): end_with_caps (:1322-1378) or close (:1206-1279).
+template <class Sink>
+LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink) {
+    const float hw = o.half_width;
+    V2 rec = w.pos[s];
+    uint32_t b0 = f2u(rec.x);
+    uint32_t flags = f2u(rec.y);
+    uint32_t m = flags & 3u;
+    bool mnec = (flags & REC_MNEC) != 0u;
+    bool close = (flags & REC_CLOSE) != 0u;
+    const bool no_fold[2] = {false, false};
+
+    if (m == 1u) {
+        if (mnec) tessellate_empty_cap(sink, slot_vertex_template(w, o, b0), o);
+        return;
+    }
+    if (m < 2u) return;
+
+    uint32_t s_p1 = next_kept_or_end(w, b0);  // second kept point
+    uint32_t s_l1 = s - 1u;                   // last kept point
+    while (slot_dropped(w, s_l1)) --s_l1;
+    uint32_t s_l2 = prev_kept(w, s_l1);
+    V2 P0 = w.pos[b0], P1 = w.pos[s_p1];
+
+    if (!(close && m > 2u)) {
+        // ---- end_with_caps ---------------------------------------------------------------------------------
+        V2 pl2 = w.pos[s_l2], pl1 = w.pos[s_l1];
+        // p0 = second to last point: its `next` side points, vertex ids and fold flags
+        Join j0;
+        if (m == 2u) {
+            first_point_side_next(P0, P1, hw, j0.next);
+            j0.fold[0] = j0.fold[1] = false;
+            j0.prev_v[0] = j0.prev_v[1] = j0.next_v[0] = j0.next_v[1] = 0xFFFFFFFFu;
+        } else {
+            uint32_t s_l3 = prev_kept(w, s_l2);
+            stream_join(w, o, s_l2, s_l3, s_l1, j0);
+            join_assign_ids(j0, slot_vertex_base<Sink>(w, s_l2, global_base));
+        }
+        // p1 = last point: side points from the edge direction (stroke.rs:1338-1346)
+        V2 p1_prev[2];
+        {
+            V2 tg = normalize(pl1 - pl2);
+            V2 n = v2(-tg.y, tg.x) * hw;
+            p1_prev[SIDE_POSITIVE] = pl1 + n;
+            p1_prev[SIDE_NEGATIVE] = pl1 - n;
+        }
+        // tessellate_last_edge (stroke.rs:2130-2206)
+        VertexTemplate vt = slot_vertex_template(w, o, s_l1);  // advancement = chain value = p0.adv + |v|
+        V2 v = pl1 - pl2;
+        uint32_t p1_prev_v[2];
+        for (int side = 0; side < 2; ++side) {
+            V2 side_position = p1_prev[side];
+            if (o.end_cap == CAP_SQUARE || o.end_cap == CAP_BUTT) {
+                float clip = o.end_cap == CAP_SQUARE ? hw : 0.0f;
+                V2 normal = normalize(pl1 - pl2);
+                LineD clip_line = line_d(pl1 + normal * clip, tangent(normal));
+                LineD side_line = line_d(side_position, side_position - j0.next[side]);
+                V2 inter;
+                if (!line_intersection(clip_line, side_line, &inter)) inter = p1_prev[side];
+                p1_prev[side] = inter;
+            }
+            p1_prev_v[side] = sink.add_vertex(vt, (p1_prev[side] - pl1) / hw, side != SIDE_POSITIVE);
+        }
+        if (m > 2u) add_edge_triangles(sink, j0.prev_v, j0.next_v, j0.fold, p1_prev_v, p1_prev_v, no_fold);
+        if (o.end_cap == CAP_ROUND)
+            tessellate_round_cap(sink, vt, pl1, hw, p1_prev[SIDE_POSITIVE] - pl1, p1_prev_v[SIDE_POSITIVE],
+                                 p1_prev_v[SIDE_NEGATIVE], v, false, o);
+        // tessellate_first_edge (stroke.rs:2208-2276): first = P0, second = P1 (firsts[1] when count > 2)
+        V2 first_next[2];
+        first_point_side_next(P0, P1, hw, first_next);
+        V2 second_prev[2];
+        uint32_t second_prev_v[2], second_next_v[2];
+        bool second_fold[2] = {false, false};
+        if (m == 2u) {
+            for (int side = 0; side < 2; ++side) {
+                second_prev[side] = p1_prev[side];
+                second_prev_v[side] = second_next_v[side] = p1_prev_v[side];
+            }
+        } else {
+            uint32_t s_p2 = next_kept_or_end(w, s_p1);
+            Join j1;
+            stream_join(w, o, s_p1, b0, s_p2, j1);
+            join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
+            for (int side = 0; side < 2; ++side) {
+                second_prev[side] = j1.prev[side];
+                second_prev_v[side] = j1.prev_v[side];
+                second_next_v[side] = j1.next_v[side];
+                second_fold[side] = j1.fold[side];
+            }
+        }
+        VertexTemplate vf = slot_vertex_template(w, o, b0);
+        uint32_t first_next_v[2];
+        for (int side = 0; side < 2; ++side) {
+            V2 side_position = first_next[side];
+            if (o.start_cap == CAP_SQUARE || o.start_cap == CAP_BUTT) {
+                float clip = o.start_cap == CAP_SQUARE ? hw : 0.0f;
+                V2 normal = normalize(P0 - P1);
+                LineD clip_line = line_d(P0 + normal * clip, tangent(normal));
+                LineD side_line = line_d(side_position, side_position - second_prev[side]);
+                V2 inter;
+                if (!line_intersection(clip_line, side_line, &inter)) inter = first_next[side];
+                side_position = inter;
+            }
+            first_next_v[side] = sink.add_vertex(vf, (side_position - P0) / hw, side != SIDE_POSITIVE);
+        }
+        {
+            const uint32_t unset[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+            add_edge_triangles(sink, unset, first_next_v, no_fold, second_prev_v, second_next_v, second_fold);
+        }
+        if (o.start_cap == CAP_ROUND)
+            tessellate_round_cap(sink, vf, P0, hw, first_next[SIDE_NEGATIVE] - P0, first_next_v[SIDE_NEGATIVE],
+                                 first_next_v[SIDE_POSITIVE], P0 - P1, true, o);
+        return;
+    }
+
+    // ---- close (count > 2) -------------------------------------------------------------------------------------
+    // firsts[0] = P0 (advancement reset to NaN), firsts[1] = P1 with the state of its stream join.
+    uint32_t s_p2 = next_kept_or_end(w, s_p1);
+    Join j1;  // firsts[1]
+    stream_join(w, o, s_p1, b0, s_p2, j1);
+    join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
+    const float start_advancement = w.adv[b0];
+    V2 A = w.pos[s_l2], B = w.pos[s_l1];
+    uint32_t s_l3 = prev_kept(w, s_l2);  // exists: m > 2
+    Join ja;                             // join at A = second to last kept point (already emitted by its slot)
+    stream_join(w, o, s_l2, s_l3, s_l1, ja);
+    join_assign_ids(ja, slot_vertex_base<Sink>(w, s_l2, global_base));
+    const bool b_fs = (w.segfs[s_l1] & SEG_FS_BIT) != 0u;
+
+    bool segment_added = !(sqlen(B - P0) < o.merge_thr);  // step(firsts[0]) merge test (stroke.rs:1531)
+    Join jc;       // the join the two extra vertices are re-created on ("p0" at stroke.rs:1248)
+    VertexTemplate vc;
+    if (segment_added) {
+        // step(P0'): join at B between A and P0
+        Join jb;
+        compute_join_fw(jb, A, B, P0, b_fs, o);
+        VertexTemplate vb = slot_vertex_template(w, o, s_l1);
+        emit_join_vertices(sink, vb, jb);
+        add_edge_triangles(sink, ja, jb);
+        tessellate_join(sink, vb, jb, o);
+        // step(P1'): join at P0' between B and P1; P0' is never a flattening step
+        compute_join_fw(jc, B, P0, P1, false, o);
+        vc = slot_vertex_template(w, o, b0);
+        vc.advancement = vb.advancement + length(P0 - B);
+        emit_join_vertices(sink, vc, jc);
+        add_edge_triangles(sink, jb, jc);
+        tessellate_join(sink, vc, jc, o);
+    } else {
+        // The closing point merged into B: B takes P0's position (stroke.rs:1228-1238), then step(P1').
+        compute_join_fw(jc, A, P0, P1, b_fs, o);
+        vc = slot_vertex_template(w, o, s_l1);
+        vc.position_on_path = P0;
+        // B's advancement was already fixed iff the join at A took the fast path (flattened_step sets
+        // next.advancement, stroke.rs:1765-1769); otherwise it is computed now from the moved position.
+        if (!ja.fast) vc.advancement = w.adv[s_l2] + length(P0 - A);
+        emit_join_vertices(sink, vc, jc);
+        add_edge_triangles(sink, ja, jc);
+        tessellate_join(sink, vc, jc, o);
+    }
+    // Re-create the two vertices towards the second endpoint with the sub-path start advancement (stroke.rs:1248-1275)
+    vc.advancement = start_advancement;
+    for (int side = 0; side < 2; ++side) {
+        V2 ref = jc.has_single[side] ? jc.single[side] : jc.next[side];
+        jc.next_v[side] = sink.add_vertex(vc, (ref - vc.position_on_path) / vc.half_width, side != SIDE_POSITIVE);
+    }
+    add_edge_triangles(sink, jc, j1);
+}
+
+}  // namespace lyc

@@ -1,0 +1,151 @@
+// emul.cpp -- CPU emulation of the CUDA pipeline, for the GPU-less build container.
+// TEST INFRASTRUCTURE ONLY.  It runs the *same* per-item functions the kernels run (stroke_core.cuh,
+// device_math.cuh compiled by g++ -ffp-contract=off) with sequential loops in place of the grid and plain
+// prefix sums in place of the decoupled look-back scans, so that the device logic can be checked against
+// the oracle without a GPU.  The product never links this; on a GPU box the -m gpu tests exercise the real
+// kernels through the C ABI.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/lyon_cuda.h"
+#include "../../lyon_b200/csrc/stroke_core.cuh"
+
+using namespace lyc;
+
+static StrokeParams make_params(const lyon_stroke_options& o, uint32_t num_attributes) {
+    StrokeParams p{};
+    p.start_cap = o.start_cap;
+    p.end_cap = o.end_cap;
+    p.line_join = o.line_join;
+    p.line_width = o.line_width;
+    p.half_width = o.line_width * 0.5f;
+    p.miter_limit = o.miter_limit;
+    p.tolerance = o.tolerance;
+    p.merge_thr = fmaxf(fminf(o.tolerance * o.tolerance * 0.5f, o.line_width * o.line_width * 0.05f), 1e-8f);
+    p.flag_thr = p.merge_thr * 5.0f;
+    p.num_attributes = num_attributes;
+    p.attr_stride = (num_attributes + 1u) / 2u;
+    p.vw_attr = num_attributes > 0 ? o.variable_line_width : -1;
+    return p;
+}
+
+extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t vertex_base,
+                                 lyon_stroke_vertex** out_v, uint64_t* n_v, uint32_t** out_i, uint64_t* n_i,
+                                 uint64_t* path_vertex_end, uint64_t* path_index_end) {
+    *out_v = nullptr;
+    *out_i = nullptr;
+    *n_v = *n_i = 0;
+    StrokeParams p = make_params(*o, b->num_attributes);
+    const uint32_t NV = b->n_verbs;
+    std::vector<uint32_t> seg_pt(NV + 1), seg_off(NV + 1), seg_id(NV + 1);
+    std::vector<float> seg_tsplit(NV + 1);
+    Views w{};
+    w.verbs = b->verbs;
+    w.points = reinterpret_cast<const V2*>(b->points);
+    w.n_verbs = NV;
+    w.seg_pt = seg_pt.data();
+    w.seg_off = seg_off.data();
+    w.seg_tsplit = seg_tsplit.data();
+    w.seg_id = seg_id.data();
+    // K1
+    uint64_t pt = 0, so = 0;
+    for (uint32_t v = 0; v < NV; ++v) {
+        uint8_t verb = b->verbs[v];
+        seg_pt[v] = (uint32_t)pt;
+        seg_off[v] = (uint32_t)so;
+        float ts;
+        so += seg_slot_count(verb, w.points, (uint32_t)pt, p.attr_stride, p.tolerance, &ts);
+        seg_tsplit[v] = ts;
+        pt += verb_point_count(verb, p.attr_stride);
+    }
+    seg_pt[NV] = (uint32_t)pt;
+    seg_off[NV] = (uint32_t)so;
+    if (so >= 0xFFFFFFF0ull) return LYON_ERR_TOO_MANY_VERTICES;
+    const uint32_t NS = (uint32_t)so;
+    std::vector<V2> pos(NS + 1);
+    std::vector<float> t(NS + 1), len(NS + 1), adv(NS + 1);
+    std::vector<uint32_t> segfs(NS + 1), voff(NS + 1), toff(NS + 1);
+    w.pos = pos.data();
+    w.t = t.data();
+    w.segfs = segfs.data();
+    w.len = len.data();
+    w.adv = adv.data();
+    w.voff = voff.data();
+    w.toff = toff.data();
+    w.n_slots = NS;
+    // K2
+    for (uint32_t v = 0; v < NV; ++v)
+        for (uint32_t s = seg_off[v]; s < seg_off[v + 1]; ++s) point_gen_slot(w, p, v, s, s - seg_off[v]);
+    // K3
+    for (uint32_t path = 0; path < b->n_paths; ++path) path_walk(w, p, b->path_verb_begin[path], b->path_verb_begin[path + 1]);
+    // K4
+    uint64_t tv = 0, tt = 0;
+    for (uint32_t s = 0; s < NS; ++s) {
+        CountSink sink;
+        sink.nv = sink.nt = 0;
+        sink.base = 0;
+        stroke_slot(w, p, s, 0u, sink);
+        voff[s] = (uint32_t)tv;
+        toff[s] = (uint32_t)tt;
+        tv += sink.nv;
+        tt += sink.nt;
+    }
+    voff[NS] = (uint32_t)tv;
+    toff[NS] = (uint32_t)tt;
+    if (tv > 0xFFFFFFFFull || tt > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (tv && vertex_base + tv - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    // K5
+    GpuVertex* V = (GpuVertex*)malloc((tv ? tv : 1) * sizeof(GpuVertex));
+    uint32_t* I = (uint32_t*)malloc((tt ? tt : 1) * 12);
+    int status = LYON_OK;
+    for (uint32_t s = 0; s < NS; ++s) {
+        uint32_t nv = voff[s + 1] - voff[s], nt = toff[s + 1] - toff[s];
+        if ((nv | nt) == 0) continue;
+        EmitSink sink;
+        sink.vtx = V + voff[s];
+        sink.idx = I + 3ull * toff[s];
+        sink.nv = sink.nt = 0;
+        sink.base = (uint32_t)vertex_base + voff[s];
+        stroke_slot(w, p, s, (uint32_t)vertex_base, sink);
+        if (sink.nv != nv || sink.nt != nt) status = LYON_ERR_INTERNAL;
+    }
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        uint32_t s_end = seg_off[b->path_verb_begin[path + 1]];
+        if (path_vertex_end) path_vertex_end[path] = voff[s_end];
+        if (path_index_end) path_index_end[path] = 3ull * toff[s_end];
+    }
+    *out_v = (lyon_stroke_vertex*)V;
+    *out_i = I;
+    *n_v = tv;
+    *n_i = 3ull * tt;
+    return status;
+}
+extern "C" void emul_free(void* p) { free(p); }
+
+// Flatten a batch of standalone curves with the device routines (k_flat_count / k_flat_emit logic).
+extern "C" uint64_t emul_flatten(const float* ctrl, uint64_t n, int npts, float tol, uint64_t* offsets, float* points, float* t_out) {
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* c = ctrl + 2 * npts * i;
+        uint32_t cnt = npts == 4 ? to_u32_or_1(cubic_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol))
+                                 : to_u32_or_1(quad_wang(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol));
+        offsets[i] = off;
+        if (points) {
+            for (uint32_t k = 0; k < cnt; ++k) {
+                V2 pos, prev;
+                float t;
+                if (npts == 4)
+                    cubic_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol, k, &pos, &prev, &t);
+                else
+                    quad_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol, k, &pos, &prev, &t);
+                points[2 * (off + k)] = pos.x;
+                points[2 * (off + k) + 1] = pos.y;
+                if (t_out) t_out[off + k] = t;
+            }
+        }
+        off += cnt;
+    }
+    offsets[n] = off;
+    return off;
+}
