@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native stroke tessellator / flattener.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the CPU arm: oracle restatement of lyon)
+
+Workload (BASELINE.json configs[2], "C3"): 1M synthetic paths x 64 mixed line/quad/cubic segments, stroke width 2,
+round joins + round caps, tolerance 0.1.  STRONG scaling: the 1M-path batch is partitioned across the N GPUs by
+cumulative segment count; the only collective is an all-gather of per-rank vertex/index totals between the count and
+the emit pass (global index rebasing).  A "step" = count passes + scans + emit pass over the rank's whole slice, inputs
+already resident in HBM.  `value` = output vertices of all ranks / max-over-ranks device time.
+
+Also reported on the same JSON line:
+  e2e           the same metric through the host-buffer API (pinned host inputs, H2D, kernels, D2H of all output)
+  roofline      emit kernel: (32 B/vertex + 4 B/index) / CUDA-event time of the emit launch vs measured HBM copy peak
+  cpu_baseline  CPU restatement of lyon (oracle/) on the box's cores, bounded sample, rank 0, N=1 only
+  flatten       configs[1] ("C2"): 10M random cubics, tolerance 0.01, flatten segments/s (N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np  # noqa: E402
+
+TOTAL_PATHS = 1_000_000
+N_SEGMENTS = 64
+C2_CURVES = 10_000_000
+
+
+def stroke_options():
+    from lyon_b200 import LineCap, LineJoin, StrokeOptions
+    return StrokeOptions(line_width=2.0, line_join=LineJoin.Round, tolerance=0.1).with_line_cap(LineCap.Round)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_paths: int, threads: int):
+    """CPU restatement of lyon's StrokeTessellator (oracle/), std::thread over paths, warm pre-sized buffers."""
+    import oracle_ffi as O
+    import workloads as W
+    batch = W.c3_batch_range(0, sample_paths, N_SEGMENTS)
+    secs, nv, ni = O.stroke_batch_timed(batch, stroke_options(), threads)
+    return {"value": nv / secs, "unit": "vertices/s", "cores": threads, "kind": "port",
+            "sample": f"first {sample_paths} paths of the same C3 batch ({nv} vertices, {secs:.2f} s, warm buffers)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, timed on the host cores.  The Rust crate
+    cannot be built in this image (no cargo), so this is the oracle port of lyon (kind: port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_ffi as O
+    import workloads as W
+    threads = os.cpu_count() or 1
+    sample = args.ref_sample
+    batch = W.c3_batch_range(0, sample, N_SEGMENTS)
+    opts = stroke_options()
+    for _ in range(args.warmup):
+        O.stroke_batch_timed(batch.slice(0, min(sample, 5000)), opts, threads)
+    secs, nv = 0.0, 0
+    for _ in range(args.steps):
+        s, v, _i = O.stroke_batch_timed(batch, opts, threads)
+        secs += s
+        nv += v
+    value = nv / secs
+    line = {
+        "impl": "reference", "metric": "stroke_output_vertices_per_s", "value": value, "unit": "vertices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample_note=f"each step = first {sample} paths of the 1M-path batch"),
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": threads, "kind": "port",
+                         "sample": f"first {sample} paths per step, {threads} threads, warm pre-sized buffers"},
+        "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, sample_note=None):
+    cfg = {
+        "workload": "C3: 1M synthetic paths x 64 mixed line/quad/cubic segments, stroke width 2, round joins+caps, tol 0.1",
+        "total_paths": TOTAL_PATHS, "segments_per_path": N_SEGMENTS, "parallelism": f"paths partitioned over {n_gpus} GPU(s)",
+        "l2": "working set (inputs+intermediates+outputs, tens of GB per step) far exceeds the 126 MB L2; no flush needed",
+    }
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--paths", type=int, default=TOTAL_PATHS, help="total paths of the batch (default: the full C3 size)")
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--ref-sample", type=int, default=200_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flatten", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import workloads as W
+    from lyon_b200 import DeviceTessellator, HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: int) -> int:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    # ---- this rank's slice: every path has the same number of segments, so the cumulative-segment partition
+    # (workloads.partition_by_cost) is an equal split of path indices; each rank generates only its own slice.
+    total_paths = args.paths
+    per = total_paths // world
+    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else total_paths
+    batch = W.c3_batch_range(lo, hi, N_SEGMENTS)
+    opts = stroke_options()
+    tz = DeviceTessellator(local_rank)
+    dbatch = tz.upload(batch)
+    torch.cuda.synchronize()
+
+    verts = idx = None
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+
+    def step(ev=None):
+        nonlocal verts, idx
+        if ev:
+            ev[0].record()
+        nv, ni = tz.stroke_plan(dbatch, opts)
+        base = 0
+        if world > 1:  # global index rebasing: all-gather of {V_r, I_r}, base = sum of V_q for q < r
+            totals[0], totals[1] = nv, ni
+            dist.all_gather_into_tensor(gathered, totals)
+            g = gathered.cpu().numpy().reshape(world, 2)
+            base = int(g[:rank, 0].sum())
+        if verts is None or verts.shape[0] < nv or idx.shape[0] < ni:
+            verts = torch.empty((nv, 8), dtype=torch.float32, device=dev)
+            idx = torch.empty((ni,), dtype=torch.int32, device=dev)
+        if ev:
+            ev[1].record()
+        tz.stroke_emit(nv, ni, vertex_base=base, vertices=verts, indices=idx)
+        if ev:
+            ev[2].record()
+        return nv, ni
+
+    for _ in range(max(args.warmup, 3)):
+        nv, ni = step()
+    torch.cuda.synchronize()
+    tz.check()
+
+    launches0 = tz.launch_count()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        nv, ni = step(events[k])
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    tz.check()
+    launches = tz.launch_count() - launches0
+    dev_ms = events[0][0].elapsed_time(events[-1][2])
+    emit_ms = sum(e[1].elapsed_time(e[2]) for e in events) / args.steps
+    plan_ms = sum(e[0].elapsed_time(e[1]) for e in events) / args.steps
+    ms_per_step = max_over_ranks(dev_ms / args.steps)
+    total_v = sum_over_ranks(nv)
+    total_i = sum_over_ranks(ni)
+    value = total_v / (ms_per_step * 1e-3)
+
+    peak, peak_src = measured_peaks()
+    emit_bytes = 32 * nv + 4 * ni
+    emit_gbs = emit_bytes / (emit_ms * 1e-3) / 1e9
+    in_bytes = dbatch.input_bytes()
+    roofline = {
+        "bound": "hbm", "kernel": "k_emit", "achieved": emit_gbs, "peak": peak, "unit": "GB/s", "frac": emit_gbs / peak,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": emit_bytes, "emit_ms": emit_ms, "plan_ms": plan_ms,
+        "whole_step_gbs": (in_bytes + emit_bytes) / (dev_ms / args.steps * 1e-3) / 1e9,
+        "whole_step_frac": (in_bytes + emit_bytes) / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+        "frac_of_nominal_8TBs": emit_gbs / 8000.0,
+    }
+
+    # ---- e2e: host buffers in, host buffers out, PCIe copies inside the timed region -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        del verts, idx
+        verts = idx = None
+        torch.cuda.empty_cache()
+        pipe = HostPipeline(local_rank, chunk_paths=25000)
+        pipe.stage(batch)
+        pipe.run(opts)  # warm-up: sizes + pins the output arrays
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ev, ei = pipe.run(opts)
+        torch.cuda.synchronize()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        e2e = {"value": sum_over_ranks(ev) / e2e_s, "unit": "vertices/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_s * 1e3, "api": "HostPipeline.run (chunked "
+               "tessellate_paths: pinned host inputs -> H2D -> plan/emit -> D2H of every vertex and index)"}
+        del pipe
+        torch.cuda.empty_cache()
+
+    flatten = None
+    if world == 1 and not args.no_flatten:
+        flatten = bench_flatten(tz, torch, dev, peak, args)
+
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        cpu = cpu_baseline(min(args.cpu_sample, total_paths), os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {
+            "metric": "stroke_output_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "flatten": flatten,
+            "output": {"vertices": total_v, "indices": total_i, "bytes": 32 * total_v + 4 * total_i},
+            "wall_ms_per_step": 1e3 * t_wall / args.steps, "workspace_bytes": tz.workspace_bytes(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_flatten(tz, torch, dev, peak, args):
+    """C2: 10M random cubics, tolerance 0.01 -> flatten segments/s on one B200."""
+    import workloads as W
+    ctrl = W.c2_cubics(C2_CURVES)
+    d = torch.from_numpy(ctrl).to(dev)
+    tol = 0.01
+    for _ in range(3):
+        off, pts = tz.flatten_curves(d, 4, tol)
+    torch.cuda.synchronize()
+    total = int(pts.shape[0])
+    steps = max(args.steps, 3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(steps):
+        off, pts = tz.flatten_curves(d, 4, tol)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    # emit kernel alone
+    import ctypes
+    e2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e2[0].record()
+    for _ in range(steps):
+        tz.L.lyon_cuda_flatten_cubics_emit(tz.ctx, d.data_ptr(), C2_CURVES, ctypes.c_float(tol), off.data_ptr(), total,
+                                           pts.data_ptr(), None)
+    e2[1].record()
+    torch.cuda.synchronize()
+    emit_ms = e2[0].elapsed_time(e2[1]) / steps
+    alg = 32 * C2_CURVES + 8 * total
+    counts = (off[1:] - off[:-1])
+    return {"metric": "flatten_segments_per_s", "value": total / (ms * 1e-3), "unit": "segments/s",
+            "workload": "C2: 10M random cubics (seed 1234), tolerance 0.01", "segments": total, "ms_per_step": ms,
+            "mean_segments_per_curve": total / C2_CURVES, "max_segments_per_curve": int(counts.max()),
+            "lut_fraction": float((counts <= 24).float().mean()),
+            "roofline": {"bound": "hbm", "kernel": "k_flat_emit", "achieved": alg / (emit_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (emit_ms * 1e-3) / 1e9 / peak, "emit_ms": emit_ms,
+                         "algorithmic_bytes_per_launch": alg, "traffic": None}}
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,8 @@ typedef struct {
 } lyon_path_batch;
 
 /* ---- context ------------------------------------------------------------------------------------- */
-/* `stream` may be NULL (the context creates its own) or an existing cudaStream_t to launch on. */
+/* `stream` is the cudaStream_t every kernel and copy of the context is issued on; NULL is CUDA's default
+ * stream.  The context never creates or destroys streams. */
 int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out);
 void lyon_cuda_destroy(lyon_cuda_ctx* ctx);
 int lyon_cuda_set_stream(lyon_cuda_ctx* ctx, void* stream);

@@ -384,7 +384,6 @@ struct DevBuf {
 struct lyon_cuda_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
     std::string err;
     uint64_t launches = 0;
     // workspace
@@ -511,15 +510,7 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return LYON_ERR_CUDA;
     lyon_cuda_ctx* c = new lyon_cuda_ctx();
     c->device = device;
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            delete c;
-            return LYON_ERR_CUDA;
-        }
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)stream;  // NULL is CUDA's default stream
     if (cudaMallocHost((void**)&c->h_totals, sizeof(Totals)) != cudaSuccess) {
         delete c;
         return LYON_ERR_CUDA;
@@ -537,21 +528,13 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int lyon_cuda_set_stream(lyon_cuda_ctx* c, void* stream) {
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    c->own_stream = false;
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        CU_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)stream;
     return LYON_OK;
 }
 int lyon_cuda_synchronize(lyon_cuda_ctx* c) {

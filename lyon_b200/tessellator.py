@@ -1,0 +1,367 @@
+"""Host-side mirror of lyon's stroke/flatten entry points over the CUDA C ABI.
+
+  StrokeTessellator.tessellate_path(path, options)      <- stroke.rs:164-177
+  tessellate_paths(paths | PathBatch, options)          <- the north-star batch API:
+      result == for p in paths { StrokeTessellator::new().tessellate_path(p, opts, &mut BuffersBuilder::new(&mut out, ctor)) }
+  flatten_cubics / flatten_quadratics                   <- CubicBezierSegment::flattened (cubic_bezier.rs:563-614) batched
+
+`DeviceTessellator` is the HBM-resident flavour (torch tensors in, torch tensors out) used by bench.py and
+by multi-GPU sharding; the plain functions move host numpy arrays across PCIe around it.
+PyTorch is only used for device memory and streams."""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _ffi
+from .geometry import STROKE_VERTEX_DTYPE, TessellationError, TooManyVertices, VertexBuffers
+from .options import StrokeOptions
+from .path import Path, PathBatch
+
+
+def _raise(L, ctx, code: int):
+    msg = L.lyon_cuda_last_error(ctx)
+    msg = msg.decode() if msg else ""
+    names = {-1: "UnsupportedParameter", -2: "TooManyVertices", -3: "Internal", -4: "CudaError",
+             -5: "InvalidArgument", -6: "OutOfMemory"}
+    what = f"{names.get(code, 'Error')}: {msg}" if msg else names.get(code, "Error")
+    if code == _ffi.ERR_TOO_MANY_VERTICES:
+        raise TooManyVertices(code, what)
+    raise TessellationError(code, what)
+
+
+class DeviceBatch:
+    """A PathBatch resident in HBM (torch uint8/float32/int32 tensors)."""
+
+    def __init__(self, batch: PathBatch, device, pinned: bool = False):
+        import torch
+
+        self.n_paths = batch.n_paths
+        self.num_attributes = batch.num_attributes
+        self.n_verbs = int(batch.verbs.shape[0])
+        self.n_points = int(batch.points.shape[0])
+
+        def up(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(a).view(dt))
+            if pinned:
+                t = t.pin_memory()
+            return t.to(device, non_blocking=pinned)
+
+        self.verbs = up(batch.verbs, np.uint8)
+        self.points = up(batch.points.reshape(-1), np.float32)
+        self.path_verb_begin = up(batch.path_verb_begin, np.int32)
+        self.path_point_begin = up(batch.path_point_begin, np.int32)
+
+    def c_struct(self) -> _ffi.CPathBatch:
+        return _ffi.CPathBatch(self.verbs.data_ptr(), self.points.data_ptr(), self.path_verb_begin.data_ptr(),
+                               self.path_point_begin.data_ptr(), self.n_paths, self.num_attributes, self.n_verbs,
+                               self.n_points)
+
+    def input_bytes(self) -> int:
+        return self.n_verbs + 8 * self.n_points + 8 * (self.n_paths + 1)
+
+
+class DeviceTessellator:
+    """One CUDA context (device + stream + grow-only workspace).  Not thread-safe, like `&mut StrokeTessellator`."""
+
+    def __init__(self, device: Union[int, str, None] = None, stream=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("lyon_b200 needs a CUDA device; there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        self.L = _ffi.lib()
+        self.ctx = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            # launch on torch's current stream (or the given torch stream) so torch ops and events order with ours
+            self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+            st = self.L.lyon_cuda_create(self.device.index, ctypes.c_void_p(self.stream.cuda_stream),
+                                         ctypes.byref(self.ctx))
+        if st != 0:
+            raise TessellationError(st, "lyon_cuda_create failed")
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.L.lyon_cuda_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stroke ---------------------------------------------------------------------------------------
+    def upload(self, batch: PathBatch, pinned: bool = False) -> DeviceBatch:
+        return DeviceBatch(batch, self.device, pinned)
+
+    def stroke_plan(self, dbatch: DeviceBatch, options: StrokeOptions):
+        """Count passes + scans. Returns (n_vertices, n_indices)."""
+        nv, ni = ctypes.c_uint64(), ctypes.c_uint64()
+        cb, co = dbatch.c_struct(), options.to_c()
+        st = self.L.lyon_cuda_stroke_plan(self.ctx, ctypes.byref(cb), ctypes.byref(co), ctypes.byref(nv), ctypes.byref(ni))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        self._planned = dbatch  # keep the device inputs alive until emit
+        return nv.value, ni.value
+
+    def stroke_emit(self, n_vertices: int, n_indices: int, vertex_base: int = 0, vertices=None, indices=None,
+                    with_ranges: bool = False):
+        """Emit pass into (given or freshly allocated) device tensors: vertices float32 [V, 8] (the 32-byte
+        lyon_stroke_vertex rows), indices int32 [I] (u32 bit patterns)."""
+        torch = self.torch
+        if vertices is None:
+            vertices = torch.empty((n_vertices, 8), dtype=torch.float32, device=self.device)
+        if indices is None:
+            indices = torch.empty((n_indices,), dtype=torch.int32, device=self.device)
+        pve = pie = None
+        if with_ranges:
+            pve = torch.empty((self._planned.n_paths,), dtype=torch.int64, device=self.device)
+            pie = torch.empty((self._planned.n_paths,), dtype=torch.int64, device=self.device)
+        st = self.L.lyon_cuda_stroke_emit(self.ctx, vertices.data_ptr(), indices.data_ptr(), vertex_base,
+                                          pve.data_ptr() if with_ranges else None, pie.data_ptr() if with_ranges else None)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        if with_ranges:
+            return vertices, indices, pve, pie
+        return vertices, indices
+
+    def check(self):
+        st = self.L.lyon_cuda_check(self.ctx)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+
+    def stroke(self, dbatch: DeviceBatch, options: StrokeOptions, vertex_base: int = 0, with_ranges: bool = False):
+        nv, ni = self.stroke_plan(dbatch, options)
+        return self.stroke_emit(nv, ni, vertex_base, with_ranges=with_ranges)
+
+    # ---- flatten --------------------------------------------------------------------------------------
+    def flatten_curves(self, d_ctrl, npts: int, tolerance: float, with_t: bool = False):
+        """d_ctrl: float32 device tensor [n, 2*npts] (npts = 4 cubic / 3 quadratic).
+        Returns (offsets int64 [n+1], points float32 [total, 2][, t float32 [total]]) on the device."""
+        torch = self.torch
+        n = int(d_ctrl.shape[0])
+        offsets = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+        total = ctypes.c_uint64()
+        cnt = self.L.lyon_cuda_flatten_cubics_count if npts == 4 else self.L.lyon_cuda_flatten_quadratics_count
+        emit = self.L.lyon_cuda_flatten_cubics_emit if npts == 4 else self.L.lyon_cuda_flatten_quadratics_emit
+        st = cnt(self.ctx, d_ctrl.data_ptr(), n, tolerance, offsets.data_ptr(), ctypes.byref(total))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        pts = torch.empty((total.value, 2), dtype=torch.float32, device=self.device)
+        t = torch.empty((total.value,), dtype=torch.float32, device=self.device) if with_t else None
+        st = emit(self.ctx, d_ctrl.data_ptr(), n, tolerance, offsets.data_ptr(), total.value, pts.data_ptr(),
+                  t.data_ptr() if with_t else None)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return (offsets, pts, t) if with_t else (offsets, pts)
+
+    def launch_count(self) -> int:
+        return int(self.L.lyon_cuda_launch_count(self.ctx))
+
+    def workspace_bytes(self) -> int:
+        return int(self.L.lyon_cuda_workspace_bytes(self.ctx))
+
+    def synchronize(self):
+        self.L.lyon_cuda_synchronize(self.ctx)
+
+
+_DEFAULT: Optional[DeviceTessellator] = None
+
+
+def _default() -> DeviceTessellator:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = DeviceTessellator()
+    return _DEFAULT
+
+
+def _as_batch(paths) -> PathBatch:
+    if isinstance(paths, PathBatch):
+        return paths
+    if isinstance(paths, Path):
+        return PathBatch.from_paths([paths])
+    return PathBatch.from_paths(list(paths))
+
+
+def tessellate_paths(paths: Union[PathBatch, Iterable[Path]], options: StrokeOptions,
+                     tessellator: Optional[DeviceTessellator] = None) -> VertexBuffers:
+    """`lyon_cuda::tessellate_paths(&[Path], &StrokeOptions) -> VertexBuffers<StrokeVertexGpu, u32>` with host
+    buffers in and out, through the single C entry point lyon_cuda_tessellate_paths."""
+    tz = tessellator or _default()
+    batch = _as_batch(paths)
+    L = tz.L
+    verbs = np.ascontiguousarray(batch.verbs, np.uint8)
+    pts = np.ascontiguousarray(batch.points, np.float32)
+    vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32)
+    pb = np.ascontiguousarray(batch.path_point_begin, np.uint32)
+    cb = _ffi.CPathBatch(verbs.ctypes.data, pts.ctypes.data, vb.ctypes.data, pb.ctypes.data, batch.n_paths,
+                         batch.num_attributes, verbs.shape[0], pts.shape[0])
+    co = options.to_c()
+    pv, pi = ctypes.c_void_p(), ctypes.c_void_p()
+    nv, ni = ctypes.c_uint64(), ctypes.c_uint64()
+    with tz.torch.cuda.device(tz.device):
+        st = L.lyon_cuda_tessellate_paths(tz.ctx, ctypes.byref(cb), ctypes.byref(co), ctypes.byref(pv), ctypes.byref(nv),
+                                          ctypes.byref(pi), ctypes.byref(ni))
+    if st != 0:
+        _raise(L, tz.ctx, st)
+    try:
+        v = np.frombuffer(ctypes.string_at(pv.value, nv.value * 32), dtype=STROKE_VERTEX_DTYPE).copy() if nv.value else \
+            np.zeros(0, STROKE_VERTEX_DTYPE)
+        i = np.frombuffer(ctypes.string_at(pi.value, ni.value * 4), dtype=np.uint32).copy() if ni.value else \
+            np.zeros(0, np.uint32)
+    finally:
+        if pv.value:
+            L.lyon_cuda_free_host(pv)
+        if pi.value:
+            L.lyon_cuda_free_host(pi)
+    return VertexBuffers(v, i)
+
+
+class StrokeTessellator:
+    """`lyon_tessellation::StrokeTessellator` (stroke.rs:108-308) for single paths."""
+
+    def __init__(self, tessellator: Optional[DeviceTessellator] = None):
+        self._tz = tessellator
+
+    def tessellate_path(self, path: Path, options: StrokeOptions) -> VertexBuffers:
+        return tessellate_paths([path], options, self._tz)
+
+    tessellate = tessellate_path
+
+
+def device_mesh_to_host(vertices, indices) -> VertexBuffers:
+    """Device tensors of DeviceTessellator.stroke_emit -> host VertexBuffers."""
+    v = vertices.cpu().numpy().view(STROKE_VERTEX_DTYPE).reshape(-1)
+    i = indices.cpu().numpy().view(np.uint32)
+    return VertexBuffers(v, i)
+
+
+def flatten_cubics(ctrl: np.ndarray, tolerance: float, tessellator: Optional[DeviceTessellator] = None, with_t=False):
+    """Batched `CubicBezierSegment::flattened(tolerance)`: ctrl [n, 8] f32 -> (offsets u64 [n+1], points f32 [total, 2])."""
+    tz = tessellator or _default()
+    d = tz.torch.from_numpy(np.ascontiguousarray(ctrl, np.float32).reshape(-1, 8)).to(tz.device)
+    out = tz.flatten_curves(d, 4, tolerance, with_t)
+    return tuple(x.cpu().numpy().view(np.uint64) if k == 0 else x.cpu().numpy() for k, x in enumerate(out))
+
+
+def flatten_quadratics(ctrl: np.ndarray, tolerance: float, tessellator: Optional[DeviceTessellator] = None, with_t=False):
+    tz = tessellator or _default()
+    d = tz.torch.from_numpy(np.ascontiguousarray(ctrl, np.float32).reshape(-1, 6)).to(tz.device)
+    out = tz.flatten_curves(d, 3, tolerance, with_t)
+    return tuple(x.cpu().numpy().view(np.uint64) if k == 0 else x.cpu().numpy() for k, x in enumerate(out))
+
+
+class HostPipeline:
+    """End-to-end host->host tessellation of a large batch: the public call a lyon user makes
+    (`tessellate_paths(&[Path], &StrokeOptions) -> VertexBuffers`) for batches whose output does not have to fit
+    (or wait) in one piece.  The batch is cut into chunks of paths; two contexts on two streams alternate so that
+    the PCIe download of chunk i overlaps the upload + kernels of chunk i+1.  Chunk c is emitted with
+    vertex_base = vertices of chunks < c, so the concatenated host buffers equal the one-shot result.
+
+    Inputs are staged in pinned host memory once (`stage`), outputs land in pinned host arrays that are reused
+    across calls (like bench/tess reuses its VertexBuffers)."""
+
+    def __init__(self, device=None, chunk_paths: int = 32768):
+        import torch
+
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.chunk_paths = int(chunk_paths)
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+            self.tz = [DeviceTessellator(self.device.index, stream=s) for s in self.streams]
+        self.dev_v = [None, None]
+        self.dev_i = [None, None]
+        self.out_v = None
+        self.out_i = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def stage(self, batch: PathBatch):
+        """Pin the input batch (outside any timed region) and precompute chunk boundaries."""
+        torch = self.torch
+        self.batch = batch
+        self.p_verbs = torch.from_numpy(np.ascontiguousarray(batch.verbs, np.uint8)).pin_memory()
+        self.p_points = torch.from_numpy(np.ascontiguousarray(batch.points, np.float32).reshape(-1)).pin_memory()
+        self.vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32).astype(np.int64)
+        self.pb = np.ascontiguousarray(batch.path_point_begin, np.uint32).astype(np.int64)
+        n = batch.n_paths
+        self.cuts = list(range(0, n, self.chunk_paths)) + [n]
+        self.p_ranges = []
+        for lo, hi in zip(self.cuts[:-1], self.cuts[1:]):
+            r = torch.from_numpy((self.vb[lo:hi + 1] - self.vb[lo]).astype(np.int32)).pin_memory()
+            self.p_ranges.append(r)
+
+    def _ensure(self, which, k, rows, cols, dtype):
+        torch = self.torch
+        cur = (self.dev_v if which == "v" else self.dev_i)[k]
+        if cur is None or cur.shape[0] < rows:
+            shape = (int(rows * 1.1) + 16, cols) if cols else (int(rows * 1.1) + 16,)
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            (self.dev_v if which == "v" else self.dev_i)[k] = t
+            return t
+        return cur
+
+    def run(self, options: StrokeOptions):
+        """One end-to-end pass. Returns (n_vertices, n_indices); results are in self.out_v[:nv], self.out_i[:ni]."""
+        torch = self.torch
+        batch = self.batch
+        tot_v = tot_i = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+        with torch.cuda.device(self.device):
+            for c, (lo, hi) in enumerate(zip(self.cuts[:-1], self.cuts[1:])):
+                k = c & 1
+                s, tz = self.streams[k], self.tz[k]
+                v0, v1, p0, p1 = int(self.vb[lo]), int(self.vb[hi]), int(self.pb[lo]), int(self.pb[hi])
+                with torch.cuda.stream(s):
+                    d = DeviceBatch.__new__(DeviceBatch)
+                    d.n_paths, d.num_attributes, d.n_verbs, d.n_points = hi - lo, batch.num_attributes, v1 - v0, p1 - p0
+                    d.verbs = self.p_verbs[v0:v1].to(self.device, non_blocking=True)
+                    d.points = self.p_points[2 * p0:2 * p1].to(self.device, non_blocking=True)
+                    d.path_verb_begin = self.p_ranges[c].to(self.device, non_blocking=True)
+                    d.path_point_begin = d.path_verb_begin
+                    self.h2d_bytes += (v1 - v0) + 8 * (p1 - p0) + 4 * (hi - lo + 1)
+                    nv, ni = tz.stroke_plan(d, options)  # syncs stream k only
+                    if tot_v + nv > 0xFFFFFFFF:
+                        raise TooManyVertices(_ffi.ERR_TOO_MANY_VERTICES, "TooManyVertices")
+                    dv = self._ensure("v", k, nv, 8, torch.float32)
+                    di = self._ensure("i", k, ni, 0, torch.int32)
+                    if self.out_v is None or self.out_v.shape[0] < tot_v + nv or self.out_i.shape[0] < tot_i + ni:
+                        self._grow_outputs(tot_v + nv, tot_i + ni, c + 1, tot_v, tot_i)
+                    tz.stroke_emit(nv, ni, vertex_base=tot_v, vertices=dv, indices=di)
+                    self.out_v[tot_v:tot_v + nv].copy_(dv[:nv], non_blocking=True)
+                    self.out_i[tot_i:tot_i + ni].copy_(di[:ni], non_blocking=True)
+                    self.d2h_bytes += 32 * nv + 4 * ni
+                tot_v += nv
+                tot_i += ni
+            for s in self.streams:
+                s.synchronize()
+            for tz in self.tz:
+                tz.check()
+        return tot_v, tot_i
+
+    def _grow_outputs(self, need_v, need_i, chunks_done, have_v, have_i):
+        """Pinned output arrays sized by extrapolating from the chunks seen so far (first call only, in practice)."""
+        torch = self.torch
+        n_chunks = len(self.cuts) - 1
+        scale = n_chunks / max(chunks_done, 1) * 1.05
+        new_v = torch.empty((int(need_v * scale) + 1024, 8), dtype=torch.float32).pin_memory()
+        new_i = torch.empty((int(need_i * scale) + 4096,), dtype=torch.int32).pin_memory()
+        for s in self.streams:
+            s.synchronize()
+        if self.out_v is not None and have_v:
+            new_v[:have_v].copy_(self.out_v[:have_v])
+            new_i[:have_i].copy_(self.out_i[:have_i])
+        self.out_v, self.out_i = new_v, new_i
+
+    def result(self, nv: int, ni: int) -> VertexBuffers:
+        return VertexBuffers(self.out_v[:nv].numpy().view(STROKE_VERTEX_DTYPE).reshape(-1),
+                             self.out_i[:ni].numpy().view(np.uint32))
+
+    def launch_count(self) -> int:
+        return sum(t.launch_count() for t in self.tz)

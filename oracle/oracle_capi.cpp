@@ -57,50 +57,49 @@ void oracle_mesh_copy(const oracle_mesh* m, void* vertices, uint32_t* indices, u
 }
 void oracle_mesh_free(oracle_mesh* m) { delete m; }
 
-// Timed multi-threaded run for the CPU baseline ("rayon-parallel over paths" stand-in): paths are
-// handed out in blocks to n_threads workers, each tessellating into its own pre-reserved buffers
-// (as bench/tess pre-sizes its VertexBuffers).  Returns seconds of wall clock for the parallel
-// region only; writes total vertices / indices produced.
+// Timed multi-threaded run for the CPU baseline ("rayon-parallel over paths" stand-in): the batch is cut
+// into n_threads contiguous ranges of equal verb count; every worker tessellates its range into its own
+// VertexBuffers.  Like bench/tess (which reuses a pre-sized VertexBuffers across iterations) the buffers are
+// warm: one untimed pass sizes and touches them, they are cleared (capacity kept), and the second pass is
+// timed.  Returns seconds of wall clock of the timed parallel region; writes total vertices / indices.
 double oracle_stroke_batch_timed(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
                                  const uint32_t* path_point_begin, uint32_t n_paths, uint32_t num_attributes,
                                  const Options* opts, int n_threads, uint64_t* total_vertices,
                                  uint64_t* total_indices) {
     if (n_threads < 1) n_threads = 1;
     std::vector<Buffers> bufs((size_t)n_threads);
-    // Pre-reserve from a one-path probe (outside the timed region).
-    size_t probe_v = 64, probe_i = 192;
-    if (n_paths > 0) {
-        Buffers probe;
-        stroke_path(verbs + path_verb_begin[0], path_verb_begin[1] - path_verb_begin[0],
-                    points + 2 * (size_t)path_point_begin[0], num_attributes, *opts, probe);
-        probe_v = probe.vertices.size() * 5 / 4 + 64;
-        probe_i = probe.indices.size() * 5 / 4 + 192;
+    std::vector<uint32_t> cut((size_t)n_threads + 1, n_paths);
+    cut[0] = 0;
+    {
+        const uint64_t total_verbs = path_verb_begin[n_paths];
+        uint32_t p = 0;
+        for (int t = 1; t < n_threads; ++t) {
+            uint64_t target = total_verbs * (uint64_t)t / (uint64_t)n_threads;
+            while (p < n_paths && path_verb_begin[p] < target) ++p;
+            cut[(size_t)t] = p;
+        }
     }
-    size_t per_thread = (size_t)n_paths / (size_t)n_threads + 1;
-    for (auto& b : bufs) {
-        b.vertices.reserve(per_thread * probe_v);
-        b.indices.reserve(per_thread * probe_i);
-    }
-    std::atomic<uint32_t> next(0);
-    const uint32_t block = 256;
-    auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; ++t) {
-        th.emplace_back([&, t]() {
-            Buffers& b = bufs[(size_t)t];
-            for (;;) {
-                uint32_t s = next.fetch_add(block);
-                if (s >= n_paths) break;
-                uint32_t e = s + block < n_paths ? s + block : n_paths;
-                for (uint32_t p = s; p < e; ++p) {
+    double secs = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto& b : bufs) {
+            b.vertices.clear();
+            b.indices.clear();
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) {
+            th.emplace_back([&, t]() {
+                Buffers& b = bufs[(size_t)t];
+                for (uint32_t p = cut[(size_t)t]; p < cut[(size_t)t + 1]; ++p) {
                     uint32_t vb = path_verb_begin[p], ve = path_verb_begin[p + 1];
                     stroke_path(verbs + vb, ve - vb, points + 2 * (size_t)path_point_begin[p], num_attributes, *opts, b);
                 }
-            }
-        });
+            });
+        }
+        for (auto& x : th) x.join();
+        auto t1 = std::chrono::steady_clock::now();
+        secs = std::chrono::duration<double>(t1 - t0).count();
     }
-    for (auto& x : th) x.join();
-    auto t1 = std::chrono::steady_clock::now();
     uint64_t tv = 0, ti = 0;
     for (auto& b : bufs) {
         tv += b.vertices.size();
@@ -108,7 +107,7 @@ double oracle_stroke_batch_timed(const uint8_t* verbs, const float* points, cons
     }
     *total_vertices = tv;
     *total_indices = ti;
-    return std::chrono::duration<double>(t1 - t0).count();
+    return secs;
 }
 
 // ---- flattening -------------------------------------------------------------------------------

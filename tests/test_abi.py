@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/lyon_cuda.h declares (no compute without a GPU)."""
+import re
+
+import pytest
+
+import oracle_ffi as O
+from lyon_b200 import _ffi
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build_cuda()
+    L = _ffi.lib()
+    header = (O.ROOT / "include" / "lyon_cuda.h").read_text()
+    declared = set(re.findall(r"\b(lyon_cuda_\w+)\s*\(", header))
+    declared.discard("lyon_cuda_ctx")
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in lyon_cuda.h but not exported"
+    assert declared == set(_ffi.SYMBOLS)
+
+
+def test_struct_layouts_match_the_header():
+    import ctypes
+    from lyon_b200.geometry import STROKE_VERTEX_DTYPE
+    from lyon_b200.options import CStrokeOptions
+    assert ctypes.sizeof(CStrokeOptions) == 20
+    assert STROKE_VERTEX_DTYPE.itemsize == 32
+    assert ctypes.sizeof(_ffi.CPathBatch) == 48
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lyon_b200 import DeviceTessellator
+    with pytest.raises(RuntimeError):
+        DeviceTessellator()
+
+
+def test_product_does_not_reference_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/ or tests/emul."""
+    for f in (O.ROOT / "lyon_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h", ".cpp"):
+            txt = f.read_text()
+            for needle in ("liblyon_oracle", "libemul", "oracle_ffi", "emul_ffi", "lyon_oracle.hpp"):
+                assert needle not in txt, f"{f} references test infrastructure ({needle})"

@@ -1,0 +1,212 @@
+"""-m gpu: the real CUDA path (through the C ABI) against the oracle on the same seeded inputs, the committed
+fixtures, edge cases, and -- at BASELINE.json's full sizes -- size-independent properties."""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import workloads as W
+from lyon_b200 import LineCap, LineJoin, Path, PathBatch, StrokeOptions
+from parity import assert_mesh_parity, bbox_extent
+
+pytestmark = pytest.mark.gpu
+GOLDEN = O.ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def tz():
+    import torch
+    from lyon_b200 import DeviceTessellator
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    t = DeviceTessellator(0)
+    yield t
+    t.close()
+
+
+def gpu_stroke(tz, batch, o, vertex_base=0, with_ranges=False):
+    import torch
+    from lyon_b200 import device_mesh_to_host
+    d = tz.upload(batch)
+    out = tz.stroke(d, o, vertex_base=vertex_base, with_ranges=with_ranges)
+    torch.cuda.synchronize()
+    tz.check()
+    if with_ranges:
+        return device_mesh_to_host(out[0], out[1]), out[2].cpu().numpy().astype(np.uint64), out[3].cpu().numpy().astype(np.uint64)
+    return device_mesh_to_host(out[0], out[1])
+
+
+def all_options(tol=0.1, width=1.0):
+    for join in LineJoin:
+        for cap in LineCap:
+            yield StrokeOptions(tolerance=tol, line_width=width, line_join=join).with_line_cap(cap)
+
+
+def test_native_library_is_loaded(tz):
+    from lyon_b200 import _ffi
+    maps = open("/proc/self/maps").read()
+    assert str(_ffi.lib_path()) in maps
+    assert tz.launch_count() == 0
+
+
+@pytest.mark.parametrize("tol", [0.05, 0.1, 0.01, 0.001])
+def test_c1_fixtures(tz, tol):
+    """C1: assets/logo.path (width 1, tol 0.05, Miter/Butt) and the Rust logo (bench/tess stroke_01..03)."""
+    for path in W.fixture_paths(GOLDEN):
+        batch = PathBatch.from_paths([path])
+        for o in all_options(tol):
+            assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch), what=str(o))
+    logo = PathBatch.from_paths([W.fixture_paths(GOLDEN)[0]])
+    vb = gpu_stroke(tz, logo, StrokeOptions(tolerance=0.05))
+    assert (len(vb.vertices), len(vb.indices)) == (2546, 7554)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_adversarial_paths(tz, seed):
+    batch = W.random_small_paths(300, 1000 + seed)
+    for tol, w, ml in ((0.1, 1.0, 4.0), (0.02, 3.0, 2.0), (0.5, 0.3, 1.0)):
+        for join in LineJoin:
+            for cap in LineCap:
+                o = StrokeOptions(tolerance=tol, line_width=w, line_join=join, miter_limit=ml).with_line_cap(cap)
+                got, pve, pie = gpu_stroke(tz, batch, o, with_ranges=True)
+                want, wpve, wpie = O.stroke_batch(batch, o, with_ranges=True)
+                assert_mesh_parity(got, want, bbox_extent(batch), what=f"seed {seed} {o}")
+                assert np.array_equal(pve, wpve) and np.array_equal(pie, wpie)
+
+
+def test_edge_cases(tz):
+    o = StrokeOptions()
+    # empty batch / empty path
+    empty = PathBatch.from_paths([Path.builder().build()])
+    assert len(gpu_stroke(tz, empty, o).vertices) == 0
+    # reference's pinned counts (stroke.rs:2852-2974)
+    b = Path.builder()
+    b.begin((-1.0, 1.0)); b.line_to((1.0, 1.0)); b.line_to((1.0, -1.0)); b.line_to((-1.0, -1.0)); b.end(False)
+    b.begin((-1.0, -1.0)); b.line_to((1.0, -1.0)); b.line_to((1.0, 1.0)); b.line_to((-1.0, 1.0)); b.end(False)
+    sq = PathBatch.from_paths([b.build()])
+    assert len(gpu_stroke(tz, sq, o.with_line_join(LineJoin.Miter).with_line_cap(LineCap.Butt)).indices) == 36
+    assert len(gpu_stroke(tz, sq, o.with_line_join(LineJoin.Bevel).with_line_cap(LineCap.Square)).indices) == 48
+    b = Path.builder()
+    b.begin((1.0, 0.0)); b.end(True)
+    b.begin((2.0, 0.0)); b.line_to((2.0, 0.0)); b.end(False)
+    b.begin((3.0, 0.0)); b.line_to((3.0, 0.0)); b.end(True)
+    b.begin((3.0, 0.0)); b.line_to((3.0, 0.0)); b.line_to((3.0, 0.0)); b.line_to((3.0, 0.0)); b.end(True)
+    b.begin((4.0, 0.0)); b.end(False)
+    caps = PathBatch.from_paths([b.build()])
+    assert len(gpu_stroke(tz, caps, o.with_line_cap(LineCap.Butt)).indices) == 0
+    assert len(gpu_stroke(tz, caps, o.with_line_cap(LineCap.Square)).indices) == 24
+    for cap in LineCap:
+        assert_mesh_parity(gpu_stroke(tz, caps, o.with_line_cap(cap)), O.stroke_batch(caps, o.with_line_cap(cap)), 4.0)
+    # issue_819 closing-point snap
+    b = Path.builder()
+    b.begin((650.539978027344, 173.559997558594)); b.line_to((650.609985351562, 173.529998779297))
+    b.line_to((650.729980468750, 173.630004882812)); b.line_to((650.559997558594, 173.570007324219)); b.end(True)
+    snap = PathBatch.from_paths([b.build()])
+    for oo in all_options(0.1):
+        assert_mesh_parity(gpu_stroke(tz, snap, oo), O.stroke_batch(snap, oo), 1.0)
+    # correct_miter_clip_length: exact f32 max-y (stroke.rs:3381-3416)
+    b = Path.builder(); b.begin((-70.0, -200.0)); b.line_to((0.0, 300.0)); b.line_to((70.0, -200.0)); b.end(False)
+    mc = gpu_stroke(tz, PathBatch.from_paths([b.build()]),
+                    StrokeOptions().with_line_width(30.0).with_line_join(LineJoin.MiterClip).with_miter_limit(3.0))
+    assert mc.positions()[:, 1].max() == np.float32(345.0)
+
+
+def test_ragged_batch_and_tile_boundaries(tz):
+    """Paths of very different sizes so that sub-paths straddle scan tiles (256 slots / 256 verbs)."""
+    rng = np.random.default_rng(9)
+    paths = []
+    for n in [1, 255, 256, 257, 2, 511, 513, 1000, 3, 0, 64]:
+        b = Path.builder()
+        if n:
+            cur = rng.uniform(0, 100, 2).astype(np.float32)
+            b.begin(tuple(cur))
+            for _ in range(n):
+                cur = (cur + rng.uniform(-5, 5, 2)).astype(np.float32)
+                b.line_to(tuple(cur))
+            b.end(bool(n % 2))
+        paths.append(b.build())
+    batch = PathBatch.from_paths(paths)
+    for o in all_options(0.1, 1.5):
+        got, pve, pie = gpu_stroke(tz, batch, o, with_ranges=True)
+        want, wpve, wpie = O.stroke_batch(batch, o, with_ranges=True)
+        assert_mesh_parity(got, want, bbox_extent(batch), what=str(o))
+        assert np.array_equal(pve, wpve) and np.array_equal(pie, wpie)
+
+
+def test_c3_sample(tz):
+    """C3 at a size the oracle finishes in seconds: 20k paths x 64 mixed segments, width 2, round joins/caps."""
+    batch = W.c3_mixed_paths(20000, 64, seed=2024)
+    o = StrokeOptions(line_width=2.0, line_join=LineJoin.Round).with_line_cap(LineCap.Round)
+    assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+    batch = W.c3_mixed_paths(3000, 64, seed=11, closed_fraction=0.5)
+    assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+
+
+def test_c4_sample_fixed_width(tz):
+    """C4 geometry (1k-segment polylines, 10% reversals, miter limit 4, butt caps) on the fixed-width path."""
+    batch = W.c4_polylines(300, 1000, with_attribute=False)
+    o = StrokeOptions(line_join=LineJoin.Miter, miter_limit=4.0)
+    assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+    batch = W.c4_polylines(50, 1000, with_attribute=True)  # attributes present, constant width: with-ids path
+    assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+
+
+@pytest.mark.parametrize("tol", [1.0, 0.3, 0.1, 0.03, 0.01, 0.003, 0.001])
+def test_c5_tolerance_sweep(tz, tol):
+    batch = W.c5_logo_copies(W.fixture_paths(GOLDEN), 40)
+    o = StrokeOptions(tolerance=tol)
+    assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+
+
+def test_vertex_base_and_too_many_vertices(tz):
+    from lyon_b200 import TooManyVertices
+    batch = W.c3_mixed_paths(100, 8, seed=1)
+    o = StrokeOptions()
+    a = gpu_stroke(tz, batch, o)
+    b = gpu_stroke(tz, batch, o, vertex_base=12345)
+    assert np.array_equal(a.indices + np.uint32(12345), b.indices)
+    with pytest.raises(TooManyVertices):
+        gpu_stroke(tz, batch, o, vertex_base=0xFFFFFFFE)
+
+
+def test_host_buffer_entry_point(tz):
+    from lyon_b200 import StrokeTessellator, tessellate_paths
+    batch = W.random_small_paths(200, 77)
+    o = StrokeOptions(line_join=LineJoin.Round).with_line_cap(LineCap.Square)
+    assert_mesh_parity(tessellate_paths(batch, o, tz), O.stroke_batch(batch, o), bbox_extent(batch))
+    p = W.fixture_paths(GOLDEN)[0]
+    vb = StrokeTessellator(tz).tessellate_path(p, StrokeOptions(tolerance=0.05))
+    assert (len(vb.vertices), len(vb.indices)) == (2546, 7554)
+
+
+@pytest.mark.parametrize("npts", [3, 4])
+def test_flatten_curves(tz, npts):
+    from lyon_b200 import flatten_cubics, flatten_quadratics
+    rng = np.random.default_rng(3)
+    ctrl = rng.uniform(-500, 500, size=(100000, 2 * npts)).astype(np.float32)
+    ctrl[:10] = 0
+    for tol in (0.5, 0.01, 0.0005):
+        off, pts, t = (flatten_cubics if npts == 4 else flatten_quadratics)(ctrl, tol, tz, with_t=True)
+        ooff, opts, ot = (O.flatten_cubics if npts == 4 else O.flatten_quadratics)(ctrl, tol, with_t=True)
+        assert np.array_equal(off, ooff) and pts.tobytes() == opts.tobytes() and t.tobytes() == ot.tobytes()
+
+
+def test_c2_sample_and_full_size_properties(tz):
+    """C2: exact parity on 200k curves; at the full 10M curves only size-independent properties:
+    offsets == Wang counts recomputed in numpy for a sample, last point of every curve == `to`."""
+    import torch
+    from lyon_b200 import flatten_cubics
+    ctrl = W.c2_cubics(200000)
+    off, pts = flatten_cubics(ctrl, 0.01, tz)
+    ooff, opts = O.flatten_cubics(ctrl, 0.01)
+    assert np.array_equal(off, ooff) and pts.tobytes() == opts.tobytes()
+    n = 10_000_000
+    ctrl = W.c2_cubics(n)
+    d = torch.from_numpy(ctrl).cuda()
+    doff, dpts = tz.flatten_curves(d, 4, 0.01)
+    torch.cuda.synchronize()
+    counts = (doff[1:] - doff[:-1])
+    assert int(counts.min()) >= 1
+    last = dpts[(doff[1:] - 1)]
+    assert torch.equal(last, d[:, 6:8])  # test_flatten_end: last point == `to` for every curve
+    sample = np.arange(0, n, 997)
+    so, _ = O.flatten_cubics(ctrl[sample], 0.01)
+    assert np.array_equal(np.diff(so).astype(np.int64), counts[torch.from_numpy(sample).cuda()].cpu().numpy())

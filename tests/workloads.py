@@ -139,3 +139,48 @@ def random_small_paths(n_paths: int, seed: int, max_segments: int = 12, closed_f
 
 def fixture_paths(golden_dir):
     return [parse_svg_path((golden_dir / "logo.path").read_text()), parse_svg_path((golden_dir / "rust_logo.path").read_text())]
+
+
+def concat_batches(batches) -> PathBatch:
+    batches = list(batches)
+    if len(batches) == 1:
+        return batches[0]
+    vb = [np.zeros(1, np.uint64)]
+    pb = [np.zeros(1, np.uint64)]
+    v0 = p0 = 0
+    for b in batches:
+        vb.append(b.path_verb_begin[1:].astype(np.uint64) + np.uint64(v0))
+        pb.append(b.path_point_begin[1:].astype(np.uint64) + np.uint64(p0))
+        v0 += int(b.path_verb_begin[-1])
+        p0 += int(b.path_point_begin[-1])
+    assert v0 < 2**32 and p0 < 2**32
+    return PathBatch(np.concatenate([b.verbs for b in batches]), np.concatenate([b.points for b in batches]),
+                     np.concatenate(vb).astype(np.uint32), np.concatenate(pb).astype(np.uint32), batches[0].num_attributes)
+
+
+C3_CHUNK = 25000
+
+
+def c3_batch_range(lo: int, hi: int, n_segments: int = 64, seed: int = 2024) -> PathBatch:
+    """Paths [lo, hi) of the C3 workload.  The workload is defined chunk-wise (C3_CHUNK paths per chunk, chunk c
+    seeded with seed + c) so that any rank can generate exactly its own slice of the same 1M-path batch."""
+    assert lo % C3_CHUNK == 0 and (hi % C3_CHUNK == 0 or True)
+    out = []
+    c = lo // C3_CHUNK
+    pos = lo
+    while pos < hi:
+        n = min(C3_CHUNK, hi - pos)
+        b = c3_mixed_paths(C3_CHUNK, n_segments, seed=seed + c)
+        out.append(b if n == C3_CHUNK else b.slice(0, n))
+        pos += n
+        c += 1
+    return concat_batches(out)
+
+
+def partition_by_cost(path_verb_begin: np.ndarray, n_ranks: int) -> np.ndarray:
+    """Cut a batch into n_ranks contiguous path ranges of ~equal cumulative segment (verb) count.
+    Returns n_ranks + 1 path indices."""
+    total = int(path_verb_begin[-1])
+    targets = (np.arange(1, n_ranks) * total) // n_ranks
+    cuts = np.searchsorted(path_verb_begin, targets, side="left")
+    return np.concatenate([[0], cuts, [len(path_verb_begin) - 1]]).astype(np.int64)
