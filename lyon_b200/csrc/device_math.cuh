@@ -58,11 +58,19 @@ LYC_HD float fast_atan2(float y, float x) {
     return result;
 }
 LYC_HD float angle_from_x_axis(V2 v) { return fast_atan2(v.y, v.x); }
+// fmodf(x, m) for m > 0, exact like the libm routine.  |x| < m returns x; m <= |x| < 2m returns x -/+ m, which is
+// exact (Sterbenz: m <= |x| <= 2m); everything else (incl. NaN/inf) goes to fmodf.
+LYC_HD float fmod_small(float x, float m) {
+    float ax = fabsf(x);
+    if (ax < m) return x;
+    if (ax < 2.0f * m) return x < 0.0f ? x + m : x - m;
+    return fmodf(x, m);
+}
 // euclid Angle::angle_to
 LYC_HD float angle_to(float self, float to) {
     float mx = LYC_PI_F * 2.0f;
-    float d = fmodf(to - self, mx);
-    return fmodf(2.0f * d, mx) - d;
+    float d = fmod_small(to - self, mx);
+    return fmod_small(2.0f * d, mx) - d;
 }
 // Rust f32::{cos,sin,acos,asin,log2} call the platform libm; both sides evaluate in double and round
 // once (DESIGN.md "Transcendentals").

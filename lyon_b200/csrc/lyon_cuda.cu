@@ -8,8 +8,8 @@
 //   k_seg_setup     1 thread / verb        two chained decoupled-look-back scans (points, slots)
 //   k_point_gen     1 thread / slot        segment tiles, smem binary search, coalesced slot writes
 //   k_path_walk     1 thread / path        sequential f32 chains (merge filter, advancement)
-//   k_count_scan    1 thread / slot        vertex+triangle counts, fused decoupled-look-back scan
-//   k_emit          1 thread / slot        StrokeVertexGpu (2 x 16 B stores per vertex) + u32 indices
+//   k_count_tile    1 block / 256 slots    vertex+triangle counts (work redistributed in the block), fused look-back scan
+//   k_emit_tile     1 block / 256 slots    StrokeVertexGpu (2 x 16 B stores per vertex) + u32 indices, arcs 1 thread / vertex
 //   k_path_ranges   1 thread / path        per-path output ranges
 //   k_flat_count / k_flat_emit             standalone curve batches (lyon_geom flattening)
 #include <cuda_runtime.h>
@@ -216,24 +216,109 @@ __global__ void __launch_bounds__(128) k_path_walk(Views w, StrokeParams p, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K4: counts + fused scan -> voff / toff (exclusive, u32; totals in 64 bits).
+// K4 / K5: count and emit share one skeleton.  A block owns a tile of BLOCK slots and redistributes the work so
+// that warps stay converged:
+//   phase 1  one thread per slot: classify; the ~75 % flattened-curve ("fast path") joins are finished here
+//   phase 2  the slots that need the full join logic are compacted into a shared-memory list and processed by
+//            the first threads of the block (dense warps); likewise the End slots (caps / closing joins)
+//   phase 3  (emit only) round join/cap arcs were only *described* in phases 1-2; their vertices are produced
+//            one thread per arc VERTEX from a block-wide prefix over the arc sizes (f64 sincos, fully converged)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_count_scan(Views w, StrokeParams p, uint32_t* ticket, uint64_t* desc_v,
-                                                      uint64_t* desc_t, Totals* totals) {
+enum { KIND_NONE = 0, KIND_JOIN = 1, KIND_END = 2 };
+struct SlotClass {
+    int kind;
+    uint32_t sf, pk, nk;
+};
+__device__ __forceinline__ SlotClass classify_slot(const Views& w, uint32_t s) {
+    SlotClass c;
+    c.kind = KIND_NONE;
+    c.pk = c.nk = 0u;
+    c.sf = 0u;
+    if (s >= w.n_slots) return c;
+    c.sf = w.segfs[s];
+    if (c.sf & SEG_END_BIT) {
+        c.kind = KIND_END;
+        return c;
+    }
+    if ((c.sf & SEG_BEGIN_BIT) || slot_dropped(w, s)) return c;
+    c.nk = next_kept_or_end(w, s);
+    if (w.segfs[c.nk] & SEG_END_BIT) return c;  // last kept point: owned by the End slot
+    c.pk = prev_kept(w, s);
+    c.kind = KIND_JOIN;
+    return c;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_count_tile(Views w, StrokeParams p, uint8_t* __restrict__ jcode, uint32_t* ticket,
+                                                      uint64_t* desc_v, uint64_t* desc_t, Totals* totals) {
     __shared__ uint32_t s_warp[WARPS + 1];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_nfull, s_nend;
     __shared__ unsigned long long s_base_v, s_base_t;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __shared__ uint32_t s_nv[BLOCK], s_nt[BLOCK];
+    __shared__ uint8_t s_code[BLOCK];
+    __shared__ uint16_t s_full[BLOCK], s_end[BLOCK];
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(ticket, 1u);
+        s_nfull = 0u;
+        s_nend = 0u;
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t s = tile * BLOCK + threadIdx.x;
-    CountSink sink;
-    sink.nv = sink.nt = 0u;
-    sink.base = 0u;
-    if (s < w.n_slots) stroke_slot(w, p, s, 0u, sink);
+    uint32_t nv = 0u, nt = 0u;
+    uint8_t code = 0;
+    SlotClass c = classify_slot(w, s);
+    if (c.kind == KIND_JOIN) {
+        if (join_is_fast(w.pos[c.pk], w.pos[s], w.pos[c.nk], (c.sf & SEG_FS_BIT) != 0u)) {
+            nv = 2u;  // flattened_step: Positive, Negative (stroke.rs:1791-1797)
+            nt = (w.segfs[c.pk] & SEG_BEGIN_BIT) ? 0u : 2u;
+            code = JC_FAST | JC_SINGLE_POS | JC_SINGLE_NEG;
+        } else {
+            s_full[atomicAdd(&s_nfull, 1u)] = (uint16_t)threadIdx.x;
+        }
+    } else if (c.kind == KIND_END) {
+        s_end[atomicAdd(&s_nend, 1u)] = (uint16_t)threadIdx.x;
+    }
+    s_nv[threadIdx.x] = nv;
+    s_nt[threadIdx.x] = nt;
+    s_code[threadIdx.x] = code;
+    __syncthreads();
+    if (threadIdx.x < s_nfull) {  // dense: full joins
+        const uint32_t lt = s_full[threadIdx.x];
+        const uint32_t s2 = tile * BLOCK + lt;
+        SlotClass c2 = classify_slot(w, s2);
+        Join j;
+        stream_join(w, p, s2, c2.pk, c2.nk, j);
+        CountSink sink;
+        sink.nv = sink.nt = 0u;
+        sink.base = 0u;
+        VertexTemplate vt;
+        vt.position_on_path = w.pos[s2];
+        vt.half_width = p.half_width;
+        vt.advancement = 0.0f;
+        vt.src = 0u;
+        vt.t = 1.0f;
+        emit_join_vertices(sink, vt, j);
+        if (!(w.segfs[c2.pk] & SEG_BEGIN_BIT)) sink.nt += 2u;  // add_edge_triangles: always two for a fixed width
+        tessellate_join(sink, vt, j, p);
+        s_nv[lt] = sink.nv;
+        s_nt[lt] = sink.nt;
+        s_code[lt] = join_encode(j);
+    }
+    if (threadIdx.x >= BLOCK - s_nend) {  // End slots on the last threads so that both lists run concurrently
+        const uint32_t lt = s_end[BLOCK - 1u - threadIdx.x];
+        CountSink sink;
+        sink.nv = sink.nt = 0u;
+        sink.base = 0u;
+        stroke_end_slot(w, p, tile * BLOCK + lt, 0u, sink);
+        s_nv[lt] = sink.nv;
+        s_nt[lt] = sink.nt;
+    }
+    __syncthreads();
+    nv = s_nv[threadIdx.x];
+    nt = s_nt[threadIdx.x];
     uint32_t agg_v, agg_t;
-    const uint32_t lv = block_exclusive_scan(sink.nv, s_warp, &agg_v);
-    const uint32_t lt = block_exclusive_scan(sink.nt, s_warp, &agg_t);
+    const uint32_t lv = block_exclusive_scan(nv, s_warp, &agg_v);
+    const uint32_t lt_ = block_exclusive_scan(nt, s_warp, &agg_t);
     if (threadIdx.x < 32) {
         uint64_t ev = lookback_exclusive(desc_v, tile, agg_v);
         uint64_t et = lookback_exclusive(desc_t, tile, agg_t);
@@ -245,10 +330,11 @@ __global__ void __launch_bounds__(BLOCK) k_count_scan(Views w, StrokeParams p, u
     __syncthreads();
     if (s < w.n_slots) {
         w.voff[s] = (uint32_t)(s_base_v + lv);
-        w.toff[s] = (uint32_t)(s_base_t + lt);
+        w.toff[s] = (uint32_t)(s_base_t + lt_);
+        jcode[s] = s_code[threadIdx.x];
     }
     if (s == w.n_slots - 1u) {
-        const unsigned long long tv = s_base_v + lv + sink.nv, tt = s_base_t + lt + sink.nt;
+        const unsigned long long tv = s_base_v + lv + nv, tt = s_base_t + lt_ + nt;
         w.voff[w.n_slots] = (uint32_t)tv;
         w.toff[w.n_slots] = (uint32_t)tt;
         totals->vertices = tv;
@@ -256,23 +342,160 @@ __global__ void __launch_bounds__(BLOCK) k_count_scan(Views w, StrokeParams p, u
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// K5: emit.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_emit(Views w, StrokeParams p, GpuVertex* __restrict__ vertices,
-                                                uint32_t* __restrict__ indices, uint32_t vertex_base, Totals* totals) {
-    const uint32_t s = blockIdx.x * BLOCK + threadIdx.x;
-    if (s >= w.n_slots) return;
-    const uint32_t vo = w.voff[s], to = w.toff[s];
-    const uint32_t nv = w.voff[s + 1] - vo, nt = w.toff[s + 1] - to;
-    if ((nv | nt) == 0u) return;
-    EmitSink sink;
-    sink.vtx = vertices + vo;
-    sink.idx = indices + 3ull * to;
-    sink.nv = sink.nt = 0u;
-    sink.base = vertex_base + vo;
-    stroke_slot(w, p, s, vertex_base, sink);
-    if (sink.nv != nv || sink.nt != nt) atomicOr(&totals->error, 1u);  // plan/emit divergence: never expected
+// ---- emit ---------------------------------------------------------------------------------------------------
+constexpr uint32_t ARC_CAP = 640;
+struct ArcDesc {
+    float a0, a1;
+    uint32_t va, vb;
+    uint32_t total_neg;  // bit 31: Side::Negative, bits 0..30: number of vertices (2^k - 1)
+    uint32_t first_id;   // global vertex id of the arc's first vertex
+    uint32_t out_v;      // index of that vertex in the vertex array
+    uint32_t out_t;      // index of its triangle in the triangle array
+    VertexTemplate vt;
+};
+struct TileEmitSink : EmitSink {
+    ArcDesc* arcs;
+    uint32_t* n_arcs;
+    GpuVertex* vertices;
+    uint32_t* indices;
+    __device__ __forceinline__ void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb,
+                                        uint32_t total) {
+        const uint32_t slot = atomicAdd(n_arcs, 1u);
+        if (slot < ARC_CAP) {
+            ArcDesc& d = arcs[slot];
+            d.a0 = a0;
+            d.a1 = a1;
+            d.va = va;
+            d.vb = vb;
+            d.total_neg = total | (negative ? 0x80000000u : 0u);
+            d.first_id = base + nv;
+            d.out_v = (uint32_t)((vtx + nv) - vertices);
+            d.out_t = (uint32_t)(((idx + 3ull * nt) - indices) / 3ull);
+            d.vt = vt;
+            nv += total;
+            nt += total;
+        } else {
+            EmitSink::arc(vt, negative, a0, a1, va, vb, total);  // list full: produce the arc inline
+        }
+    }
+};
+
+__global__ void __launch_bounds__(BLOCK) k_emit_tile(Views w, StrokeParams p, const uint8_t* __restrict__ jcode,
+                                                     GpuVertex* __restrict__ vertices, uint32_t* __restrict__ indices,
+                                                     uint32_t vertex_base, Totals* totals) {
+    __shared__ uint32_t s_warp[WARPS + 1];
+    __shared__ uint32_t s_nfull, s_nend, s_narcs;
+    __shared__ uint16_t s_full[BLOCK], s_end[BLOCK];
+    __shared__ ArcDesc s_arcs[ARC_CAP];
+    __shared__ uint32_t s_arc_prefix[ARC_CAP + 1];
+    if (threadIdx.x == 0) {
+        s_nfull = 0u;
+        s_nend = 0u;
+        s_narcs = 0u;
+    }
+    __syncthreads();
+    const uint32_t tile = blockIdx.x;
+    const uint32_t s = tile * BLOCK + threadIdx.x;
+    bool bad = false;
+    SlotClass c = classify_slot(w, s);
+    if (c.kind == KIND_JOIN) {
+        const V2 pp = w.pos[c.pk], pj = w.pos[s], pn = w.pos[c.nk];
+        if (join_is_fast(pp, pj, pn, (c.sf & SEG_FS_BIT) != 0u)) {
+            const uint32_t vo = w.voff[s], to = w.toff[s];
+            const V2 normal = fast_join_normal(pp, pj, pn);
+            VertexTemplate vt = slot_vertex_template(w, p, s);
+            EmitSink sink;
+            sink.vtx = vertices + vo;
+            sink.idx = indices + 3ull * to;
+            sink.nv = sink.nt = 0u;
+            sink.base = vertex_base + vo;
+            Join j;
+            j.fast = true;
+            j.fold[0] = j.fold[1] = false;
+            j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, normal, false);
+            j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, -normal, true);
+            if (!(w.segfs[c.pk] & SEG_BEGIN_BIT)) {
+                Join jp;
+                join_decode_ids(jp, jcode[c.pk], vertex_base + w.voff[c.pk]);
+                add_edge_triangles(sink, jp, j);
+            }
+            bad = (sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to);
+        } else {
+            s_full[atomicAdd(&s_nfull, 1u)] = (uint16_t)threadIdx.x;
+        }
+    } else if (c.kind == KIND_END) {
+        s_end[atomicAdd(&s_nend, 1u)] = (uint16_t)threadIdx.x;
+    }
+    __syncthreads();
+    if (threadIdx.x < s_nfull || threadIdx.x >= BLOCK - s_nend) {
+        const bool is_end = !(threadIdx.x < s_nfull);
+        const uint32_t lt = is_end ? s_end[BLOCK - 1u - threadIdx.x] : s_full[threadIdx.x];
+        const uint32_t s2 = tile * BLOCK + lt;
+        const uint32_t vo = w.voff[s2], to = w.toff[s2];
+        TileEmitSink sink;
+        sink.vtx = vertices + vo;
+        sink.idx = indices + 3ull * to;
+        sink.nv = sink.nt = 0u;
+        sink.base = vertex_base + vo;
+        sink.arcs = s_arcs;
+        sink.n_arcs = &s_narcs;
+        sink.vertices = vertices;
+        sink.indices = indices;
+        if (is_end) {
+            stroke_end_slot(w, p, s2, vertex_base, sink);
+        } else {
+            SlotClass c2 = classify_slot(w, s2);
+            Join j;
+            stream_join(w, p, s2, c2.pk, c2.nk, j);
+            VertexTemplate vt = slot_vertex_template(w, p, s2);
+            emit_join_vertices(sink, vt, j);
+            if (!(w.segfs[c2.pk] & SEG_BEGIN_BIT)) edge_to_previous_join(w, p, s2, c2.pk, vertex_base, jcode, j, sink);
+            tessellate_join(sink, vt, j, p);
+        }
+        bad = bad || (sink.nv != w.voff[s2 + 1] - vo) || (sink.nt != w.toff[s2 + 1] - to);
+    }
+    if (bad) atomicOr(&totals->error, 1u);  // plan/emit divergence: never expected
+    __syncthreads();
+    // ---- phase 3: arc vertices, one thread each ------------------------------------------------------------
+    const uint32_t n_arcs = min(s_narcs, ARC_CAP);
+    if (n_arcs == 0u) return;
+    uint32_t total_arc_vertices;
+    {
+        // prefix over arc sizes: ARC_CAP <= 3 * BLOCK entries, three per thread
+        uint32_t sz[3], sum = 0u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t a = threadIdx.x * 3u + k;
+            sz[k] = a < n_arcs ? (s_arcs[a].total_neg & 0x7FFFFFFFu) : 0u;
+            sum += sz[k];
+        }
+        uint32_t excl = block_exclusive_scan(sum, s_warp, &total_arc_vertices);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t a = threadIdx.x * 3u + k;
+            if (a <= ARC_CAP) s_arc_prefix[a] = excl;
+            excl += sz[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total_arc_vertices; i += BLOCK) {
+        uint32_t lo = 0u, hi = n_arcs;  // last arc with prefix <= i
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_arc_prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const ArcDesc& d = s_arcs[lo];
+        const uint32_t j = i - s_arc_prefix[lo];
+        const uint32_t total = d.total_neg & 0x7FFFFFFFu;
+        const ArcNode n = arc_node(d.a0, d.a1, d.va, d.vb, total, d.first_id, j);
+        EmitSink sink;
+        sink.vtx = vertices + d.out_v + j;
+        sink.idx = indices + 3ull * (d.out_t + j);
+        sink.nv = sink.nt = 0u;
+        sink.base = 0u;
+        sink.add_vertex(d.vt, arc_normal(n.mid), (d.total_neg & 0x80000000u) != 0u);
+        sink.add_triangle(n.ida, n.id, n.idb);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_path_ranges(Views w, const uint32_t* __restrict__ path_verb_begin, uint32_t n_paths,
@@ -387,7 +610,7 @@ struct lyon_cuda_ctx {
     std::string err;
     uint64_t launches = 0;
     // workspace
-    DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, desc, misc;
+    DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, jcode, desc, misc;
     Totals* h_totals = nullptr;  // pinned
     // state of the last plan
     bool planned = false;
@@ -455,6 +678,7 @@ StrokeParams make_params(const lyon_stroke_options& o, uint32_t num_attributes) 
     // stroke.rs:603-605
     p.merge_thr = fmaxf(fminf(o.tolerance * o.tolerance * 0.5f, o.line_width * o.line_width * 0.05f), 1e-8f);
     p.flag_thr = p.merge_thr * 5.0f;
+    p.arc_step = circle_flattening_step(p.half_width, p.tolerance);  // host libm, same as the oracle
     p.num_attributes = num_attributes;
     p.attr_stride = (num_attributes + 1u) / 2u;
     p.vw_attr = num_attributes > 0 ? o.variable_line_width : -1;  // tessellate() forces it off, stroke.rs:878
@@ -524,7 +748,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
-                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->desc, &c->misc};
+                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->desc, &c->misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -623,6 +847,7 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     TRY(ensure(c, c->adv, ns1 * 4));
     TRY(ensure(c, c->voff, ns1 * 4));
     TRY(ensure(c, c->toff, ns1 * 4));
+    TRY(ensure(c, c->jcode, ns1));
     const unsigned stiles = grid_for(n_slots, BLOCK);
     TRY(ensure(c, c->desc, (size_t)stiles * 16));
     w.pos = (V2*)c->pos.p;
@@ -635,7 +860,7 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     k_point_gen<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params);
     k_path_walk<<<grid_for(b->n_paths, 128), 128, 0, c->stream>>>(w, c->params, b->path_verb_begin, b->n_paths);
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)stiles * 16, c->stream));
-    k_count_scan<<<stiles, BLOCK, 0, c->stream>>>(w, c->params, d_ticket(c, 1), (uint64_t*)c->desc.p,
+    k_count_tile<<<stiles, BLOCK, 0, c->stream>>>(w, c->params, (uint8_t*)c->jcode.p, d_ticket(c, 1), (uint64_t*)c->desc.p,
                                                  (uint64_t*)c->desc.p + stiles, d_totals(c));
     c->launches += 3;
     CU_TRY(c, cudaGetLastError());
@@ -666,8 +891,8 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
         return LYON_OK;
     }
     if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
-    k_emit<<<grid_for(c->views.n_slots, BLOCK), BLOCK, 0, c->stream>>>(c->views, c->params, (GpuVertex*)d_vertices, d_indices,
-                                                                      (uint32_t)vertex_base, d_totals(c));
+    k_emit_tile<<<grid_for(c->views.n_slots, BLOCK), BLOCK, 0, c->stream>>>(
+        c->views, c->params, (const uint8_t*)c->jcode.p, (GpuVertex*)d_vertices, d_indices, (uint32_t)vertex_base, d_totals(c));
     c->launches++;
     if (d_path_vertex_end || d_path_index_end) {
         k_path_ranges<<<grid_for(c->n_paths, 128), 128, 0, c->stream>>>(c->views, c->d_path_verb_begin, c->n_paths,

@@ -35,6 +35,7 @@ static const uint32_t MAX_ARC_SUBDIVISIONS = 20;  // reference recursion is unbo
 struct StrokeParams {
     uint8_t start_cap, end_cap, line_join, _pad;
     float line_width, half_width, miter_limit, tolerance;
+    float arc_step;   // circle_flattening_step(half_width, tolerance): constant for a fixed line width (host computed)
     float merge_thr;  // square_merge_threshold (stroke.rs:603-605)
     float flag_thr;   // 5 * merge_thr: conservative pre-filter, see point_gen
     uint32_t num_attributes, attr_stride;
@@ -342,6 +343,18 @@ LYC_HD void get_clip_intersections(V2 previous_normal, V2 next_normal, V2 normal
     if (!line_intersection(clip_line, next_line, i2)) *i2 = normal;
 }
 
+// flattened_step's miter normal (stroke.rs:1751-1757)
+LYC_HD V2 fast_join_normal(V2 pp, V2 pj, V2 pn) {
+    V2 prev_edge = pj - pp;
+    V2 next_edge = pn - pj;
+    V2 prev_tangent = prev_edge / length(prev_edge);
+    V2 next_tangent = next_edge / length(next_edge);
+    return compute_normal(prev_tangent, next_tangent);
+}
+LYC_HD bool join_is_fast(V2 pp, V2 pj, V2 pn, bool join_fs) {  // stroke.rs:1568-1574
+    return join_fs && dot(pj - pp, pn - pj) > 0.0f;
+}
+
 // fixed_width_step_impl's choice between flattened_step (stroke.rs:1743-1806) and
 // compute_join_side_positions_fixed_width (stroke.rs:1643-1733) for the join at `pj`.
 LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const StrokeParams& o) {
@@ -438,6 +451,22 @@ LYC_HD uint32_t join_assign_ids(Join& j, uint32_t base) {
     return n;
 }
 
+// Per-slot join layout code written by the count pass and read back by the emit pass (so that the edge
+// triangles towards the previous join do not have to recompute that join): which vertices the join owns.
+static const uint8_t JC_FAST = 1, JC_FOLD_POS = 2, JC_FOLD_NEG = 4, JC_SINGLE_POS = 8, JC_SINGLE_NEG = 16;
+LYC_HD uint8_t join_encode(const Join& j) {
+    return (uint8_t)((j.fast ? JC_FAST : 0) | (j.fold[SIDE_POSITIVE] ? JC_FOLD_POS : 0) | (j.fold[SIDE_NEGATIVE] ? JC_FOLD_NEG : 0) |
+                     (j.has_single[SIDE_POSITIVE] ? JC_SINGLE_POS : 0) | (j.has_single[SIDE_NEGATIVE] ? JC_SINGLE_NEG : 0));
+}
+LYC_HD void join_decode_ids(Join& j, uint8_t code, uint32_t base) {  // fills only what add_edge_triangles reads
+    j.fast = (code & JC_FAST) != 0;
+    j.fold[SIDE_POSITIVE] = (code & JC_FOLD_POS) != 0;
+    j.fold[SIDE_NEGATIVE] = (code & JC_FOLD_NEG) != 0;
+    j.has_single[SIDE_POSITIVE] = (code & JC_SINGLE_POS) != 0;
+    j.has_single[SIDE_NEGATIVE] = (code & JC_SINGLE_NEG) != 0;
+    join_assign_ids(j, base);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Sinks: the count pass and the emit pass run the SAME emission code against different sinks.
 // ---------------------------------------------------------------------------------------------------------
@@ -452,12 +481,49 @@ struct CountSink {
     LYC_HD uint32_t next_id() const { return base + nv; }
     LYC_HD uint32_t add_vertex(const VertexTemplate&, V2, bool) { return base + nv++; }
     LYC_HD void add_triangle(uint32_t, uint32_t, uint32_t) { nt++; }
-    LYC_HD void bulk(uint32_t vertices, uint32_t triangles) {
-        nv += vertices;
-        nt += triangles;
+    LYC_HD void arc(const VertexTemplate&, bool, float, float, uint32_t, uint32_t, uint32_t total) {
+        nv += total;
+        nt += total;
     }
     static const bool kCounting = true;
 };
+// One node of tessellate_arc's recursion (stroke.rs:2612-2653).  The recursion emits 2^k - 1 vertices in
+// PRE-ORDER, each followed by its triangle (va, v, vb).  Node j re-derives its angle interval and corner ids by
+// descending from the root with the same sequence of f32 midpoints the recursion computes, so any thread can
+// produce any arc vertex independently.
+struct ArcNode {
+    float mid;
+    uint32_t id, ida, idb;
+};
+LYC_HD ArcNode arc_node(float a0, float a1, uint32_t va, uint32_t vb, uint32_t total, uint32_t first_id, uint32_t j) {
+    float lo = a0, hi = a1;
+    uint32_t ida = va, idb = vb, base = 0u, size = total;
+    ArcNode n;
+    for (;;) {
+        n.mid = (lo + hi) * 0.5f;
+        n.id = first_id + base;
+        if (j == base) break;
+        uint32_t half = (size - 1u) >> 1;
+        if (j <= base + half) {
+            hi = n.mid;
+            idb = n.id;
+            base += 1u;
+        } else {
+            lo = n.mid;
+            ida = n.id;
+            base += 1u + half;
+        }
+        size = half;
+    }
+    n.ida = ida;
+    n.idb = idb;
+    return n;
+}
+LYC_HD V2 arc_normal(float mid) {  // vector(mid.cos(), mid.sin()), stroke.rs:2627
+    double sn, cs;
+    sincos((double)mid, &sn, &cs);
+    return v2((float)cs, (float)sn);
+}
 struct EmitSink {
     GpuVertex* vtx;  // first vertex owned by this slot
     uint32_t* idx;   // first index owned by this slot
@@ -490,7 +556,14 @@ struct EmitSink {
         d[2] = c;
         nt++;
     }
-    LYC_HD void bulk(uint32_t, uint32_t) {}
+    LYC_HD void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb, uint32_t total) {
+        const uint32_t first_id = base + nv;
+        for (uint32_t j = 0; j < total; ++j) {
+            ArcNode n = arc_node(a0, a1, va, vb, total, first_id, j);
+            add_vertex(vt, arc_normal(n.mid), negative);
+            add_triangle(n.ida, n.id, n.idb);
+        }
+    }
     static const bool kCounting = false;
 };
 
@@ -515,49 +588,30 @@ LYC_HD void add_edge_triangles(Sink& sink, const Join& a, const Join& b) {
     add_edge_triangles(sink, a.prev_v, a.next_v, a.fold, b.prev_v, b.next_v, b.fold);
 }
 
-// tessellate_arc (stroke.rs:2612-2653): 2^k - 1 vertices in PRE-ORDER, each followed by its triangle.
-// The recursion is unrolled per node: node j re-derives its angle interval and corner ids by descending
-// from the root with the same sequence of f32 midpoints the recursion computes.
 template <class Sink>
 LYC_HD void emit_arc(Sink& sink, const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb,
                      uint32_t k) {
     if (k == 0u) return;
     if (k > MAX_ARC_SUBDIVISIONS) k = MAX_ARC_SUBDIVISIONS;
-    const uint32_t total = (1u << k) - 1u;
-    if (Sink::kCounting) {
-        sink.bulk(total, total);
-        return;
-    }
-    const uint32_t first_id = sink.next_id();
-    for (uint32_t j = 0; j < total; ++j) {
-        float lo = a0, hi = a1;
-        uint32_t ida = va, idb = vb, base = 0u, size = total;
-        float mid;
-        uint32_t id;
-        for (;;) {
-            mid = (lo + hi) * 0.5f;
-            id = first_id + base;
-            if (j == base) break;
-            uint32_t half = (size - 1u) >> 1;
-            if (j <= base + half) {
-                hi = mid;
-                idb = id;
-                base += 1u;
-            } else {
-                lo = mid;
-                ida = id;
-                base += 1u + half;
-            }
-            size = half;
-        }
-        sink.add_vertex(vt, v2(libm_cos(mid), libm_sin(mid)), negative);
-        sink.add_triangle(ida, id, idb);
-    }
+    sink.arc(vt, negative, a0, a1, va, vb, (1u << k) - 1u);
 }
-LYC_HD uint32_t arc_subdivisions(float diff, float radius, float tolerance) {  // stroke.rs:2002-2004, 2488-2490
-    float stp = circle_flattening_step(radius, tolerance);
-    float num_segments = ceilf(fabsf(diff) / stp);
+// `num_segments.log2().round() as u32` (stroke.rs:2004, 2490) for the integer-valued, non-negative float that
+// ceil() produced.  For N < 2^16 the rounding is decided exactly in integers: round(log2 N) = f + [N^2 >= 2^(2f+1)]
+// with f = floor(log2 N) (log2 N is never within float rounding of f + 0.5 for such N; checked exhaustively by
+// tests/test_emulation_parity.py against the libm formulation).  Larger N, NaN and inf take the libm route.
+LYC_HD uint32_t round_log2_segments(float num_segments) {
+    if (num_segments >= 1.0f && num_segments < 65536.0f) {
+        uint32_t n = (uint32_t)num_segments;
+        uint32_t f = 0;
+        while ((2u << f) <= n) ++f;  // f = floor(log2 n)
+        return f + ((n * n >= (2u << (2u * f))) ? 1u : 0u);
+    }
     return sat_u32(roundf(libm_log2(num_segments)));
+}
+LYC_HD uint32_t arc_subdivisions(float diff, float radius, const StrokeParams& o) {  // stroke.rs:2002-2004, 2488-2490
+    float stp = radius == o.half_width ? o.arc_step : circle_flattening_step(radius, o.tolerance);
+    float num_segments = ceilf(fabsf(diff) / stp);
+    return round_log2_segments(num_segments);
 }
 
 // tessellate_round_join (stroke.rs:1968-2021)
@@ -582,7 +636,7 @@ LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Jo
         start_vertex = end_vertex;
         end_vertex = tv;
     }
-    uint32_t k = arc_subdivisions(diff, radius, o.tolerance);
+    uint32_t k = arc_subdivisions(diff, radius, o);
     emit_arc(sink, vt, side != SIDE_POSITIVE, start_angle, end_angle, start_vertex, end_vertex, k);
 }
 
@@ -640,7 +694,7 @@ LYC_HD void tessellate_round_cap(Sink& sink, VertexTemplate vt, V2 center, float
     float diff = angle_to(start_angle, angle_from_x_axis(edge_normal));
     float mid_angle = start_angle + diff;
     float end_angle = mid_angle + diff;
-    uint32_t k = arc_subdivisions(diff, radius, o.tolerance);
+    uint32_t k = arc_subdivisions(diff, radius, o);
     vt.position_on_path = center;
     vt.half_width = radius;
     uint32_t mid_vertex = sink.add_vertex(vt, normalize(edge_normal), !first_side_positive);
@@ -689,8 +743,25 @@ LYC_HD uint32_t slot_vertex_base(const Views& w, uint32_t s, uint32_t global_bas
 template <class Sink>
 LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink);
 
+// Edge triangles between the previous stream join (at kept slot pk, not a Begin) and join j at slot s.
+// With a jcode array (emit pass) the previous join's vertex layout is decoded, otherwise it is recomputed.
 template <class Sink>
-LYC_HD void stroke_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink) {
+LYC_HD void edge_to_previous_join(const Views& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t global_base,
+                                  const uint8_t* jcode, const Join& j, Sink& sink) {
+    Join jp;
+    if (jcode) {
+        join_decode_ids(jp, jcode[pk], slot_vertex_base<Sink>(w, pk, global_base));
+    } else {
+        uint32_t pk2 = prev_kept(w, pk);
+        stream_join(w, o, pk, pk2, s, jp);
+        join_assign_ids(jp, slot_vertex_base<Sink>(w, pk, global_base));
+    }
+    add_edge_triangles(sink, jp, j);
+}
+
+template <class Sink>
+LYC_HD void stroke_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink,
+                        const uint8_t* jcode = nullptr, uint8_t* jcode_out = nullptr) {
     uint32_t sf = w.segfs[s];
     if (sf & SEG_END_BIT) {
         stroke_end_slot(w, o, s, global_base, sink);
@@ -703,14 +774,10 @@ LYC_HD void stroke_slot(const Views& w, const StrokeParams& o, uint32_t s, uint3
     Join j;
     stream_join(w, o, s, pk, nk, j);
     VertexTemplate vt = slot_vertex_template(w, o, s);
+    if (jcode_out) jcode_out[s] = join_encode(j);
     emit_join_vertices(sink, vt, j);
-    if (!(w.segfs[pk] & SEG_BEGIN_BIT)) {  // count > 2: edge between the previous join and this one (stroke.rs:1611-1613)
-        uint32_t pk2 = prev_kept(w, pk);
-        Join jp;
-        stream_join(w, o, pk, pk2, s, jp);
-        join_assign_ids(jp, slot_vertex_base<Sink>(w, pk, global_base));
-        add_edge_triangles(sink, jp, j);
-    }
+    if (!(w.segfs[pk] & SEG_BEGIN_BIT))  // count > 2: edge between the previous join and this one (stroke.rs:1611-1613)
+        edge_to_previous_join(w, o, s, pk, global_base, jcode, j, sink);
     tessellate_join(sink, vt, j, o);
 }
 

@@ -24,6 +24,7 @@ static StrokeParams make_params(const lyon_stroke_options& o, uint32_t num_attri
     p.tolerance = o.tolerance;
     p.merge_thr = fmaxf(fminf(o.tolerance * o.tolerance * 0.5f, o.line_width * o.line_width * 0.05f), 1e-8f);
     p.flag_thr = p.merge_thr * 5.0f;
+    p.arc_step = circle_flattening_step(p.half_width, p.tolerance);  // host libm, same as the oracle
     p.num_attributes = num_attributes;
     p.attr_stride = (num_attributes + 1u) / 2u;
     p.vw_attr = num_attributes > 0 ? o.variable_line_width : -1;
@@ -66,6 +67,7 @@ extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_opt
     std::vector<V2> pos(NS + 1);
     std::vector<float> t(NS + 1), len(NS + 1), adv(NS + 1);
     std::vector<uint32_t> segfs(NS + 1), voff(NS + 1), toff(NS + 1);
+    std::vector<uint8_t> jcode(NS + 1, 0);
     w.pos = pos.data();
     w.t = t.data();
     w.segfs = segfs.data();
@@ -85,7 +87,7 @@ extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_opt
         CountSink sink;
         sink.nv = sink.nt = 0;
         sink.base = 0;
-        stroke_slot(w, p, s, 0u, sink);
+        stroke_slot(w, p, s, 0u, sink, nullptr, jcode.data());
         voff[s] = (uint32_t)tv;
         toff[s] = (uint32_t)tt;
         tv += sink.nv;
@@ -107,7 +109,7 @@ extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_opt
         sink.idx = I + 3ull * toff[s];
         sink.nv = sink.nt = 0;
         sink.base = (uint32_t)vertex_base + voff[s];
-        stroke_slot(w, p, s, (uint32_t)vertex_base, sink);
+        stroke_slot(w, p, s, (uint32_t)vertex_base, sink, jcode.data(), nullptr);
         if (sink.nv != nv || sink.nt != nt) status = LYON_ERR_INTERNAL;
     }
     for (uint32_t path = 0; path < b->n_paths; ++path) {
@@ -122,6 +124,8 @@ extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_opt
     return status;
 }
 extern "C" void emul_free(void* p) { free(p); }
+extern "C" uint32_t emul_round_log2_segments(float n) { return round_log2_segments(n); }
+extern "C" float emul_angle_to(float a, float b) { return angle_to(a, b); }
 
 // Flatten a batch of standalone curves with the device routines (k_flat_count / k_flat_emit logic).
 extern "C" uint64_t emul_flatten(const float* ctrl, uint64_t n, int npts, float tol, uint64_t* offsets, float* points, float* t_out) {
