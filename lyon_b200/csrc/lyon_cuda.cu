@@ -8,8 +8,8 @@
 //   k_seg_setup     1 thread / verb        two chained decoupled-look-back scans (points, slots)
 //   k_point_gen     1 thread / slot        segment tiles, smem binary search, coalesced slot writes
 //   k_path_walk     1 thread / path        sequential f32 chains (merge filter, advancement)
-//   k_count_tile    1 block / 256 slots    vertex+triangle counts (work redistributed in the block), fused look-back scan
-//   k_emit_tile     1 block / 256 slots    StrokeVertexGpu (2 x 16 B stores per vertex) + u32 indices, arcs 1 thread / vertex
+//   k_classify_count / k_full_count / k_end_count / k_scan_offsets   count pass split by slot population + in-place scan
+//   k_emit_fast / k_emit_full / k_emit_end                            emit pass, StrokeVertexGpu (2 x 16 B stores) + u32 indices
 //   k_path_ranges   1 thread / path        per-path output ranges
 //   k_flat_count / k_flat_emit             standalone curve batches (lyon_geom flattening)
 #include <cuda_runtime.h>
@@ -111,7 +111,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s
 }
 
 struct Totals {
-    unsigned long long points, slots, vertices, triangles, flat_points;
+    unsigned long long points, slots, vertices, triangles, flat_points, subpaths;
     unsigned int error;
     unsigned int _pad;
 };
@@ -120,7 +120,7 @@ struct Totals {
 // K1: per verb -- stored-point offset (scan #1), then slot count from the Wang formula (scan #2).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_seg_setup(Views w, StrokeParams p, uint32_t* ticket, uint64_t* desc_pts,
-                                                     uint64_t* desc_slots, Totals* totals) {
+                                                     uint64_t* desc_slots, uint64_t* desc_sp, Totals* totals) {
     __shared__ uint32_t s_warp[WARPS + 1];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -173,12 +173,24 @@ __global__ void __launch_bounds__(BLOCK) k_seg_setup(Views w, StrokeParams p, ui
     }
     __syncthreads();
     const unsigned long long so = s_base + local;
+    const unsigned long long slots_total = s_base + agg64;
     if (valid) w.seg_off[v] = (uint32_t)so;
+    __syncthreads();
+    // scan #3: sub-path index of every End/Close verb (stored in the verb's otherwise unused tsplit field)
+    const uint32_t is_end = (valid && (verb == VERB_END || verb == VERB_CLOSE)) ? 1u : 0u;
+    local = block_exclusive_scan(is_end, s_warp, &agg);
+    if (threadIdx.x < 32) {
+        uint64_t e = lookback_exclusive(desc_sp, tile, agg);
+        if (threadIdx.x == 0) s_base = e;
+    }
+    __syncthreads();
+    if (is_end) w.seg_tsplit[v] = __uint_as_float((uint32_t)(s_base + local));
     if (v == w.n_verbs - 1u) {
         w.seg_pt[w.n_verbs] = (uint32_t)(pt64 + npts);
-        w.seg_off[w.n_verbs] = (uint32_t)(s_base + agg64);
+        w.seg_off[w.n_verbs] = (uint32_t)slots_total;
         totals->points = pt64 + npts;
-        totals->slots = s_base + agg64;
+        totals->slots = slots_total;
+        totals->subpaths = s_base + local + is_end;
     }
 }
 
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK) k_seg_setup(Views w, StrokeParams p, ui
 // K2: per slot.  A block owns a tile of BLOCK verbs and walks their slots BLOCK at a time, so global
 // writes are slot-contiguous (coalesced) whatever the per-curve flatten counts are.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_point_gen(Views w, StrokeParams p) {
+__global__ void __launch_bounds__(BLOCK) k_point_gen(Views w, StrokeParams p, uint32_t* __restrict__ sp_end_slot) {
     __shared__ uint32_t s_off[BLOCK + 1];
     const uint32_t v0 = blockIdx.x * BLOCK;
     const uint32_t nv = min((uint32_t)BLOCK, w.n_verbs - v0);
@@ -202,6 +214,8 @@ __global__ void __launch_bounds__(BLOCK) k_point_gen(Views w, StrokeParams p) {
             if (s_off[mid] <= s) lo = mid; else hi = mid;
         }
         point_gen_slot(w, p, v0 + lo, s, s - s_off[lo]);
+        const uint8_t verb = w.verbs[v0 + lo];
+        if (verb == VERB_END || verb == VERB_CLOSE) sp_end_slot[__float_as_uint(w.seg_tsplit[v0 + lo])] = s;
     }
 }
 
@@ -216,13 +230,13 @@ __global__ void __launch_bounds__(128) k_path_walk(Views w, StrokeParams p, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K4 / K5: count and emit share one skeleton.  A block owns a tile of BLOCK slots and redistributes the work so
-// that warps stay converged:
-//   phase 1  one thread per slot: classify; the ~75 % flattened-curve ("fast path") joins are finished here
-//   phase 2  the slots that need the full join logic are compacted into a shared-memory list and processed by
-//            the first threads of the block (dense warps); likewise the End slots (caps / closing joins)
-//   phase 3  (emit only) round join/cap arcs were only *described* in phases 1-2; their vertices are produced
-//            one thread per arc VERTEX from a block-wide prefix over the arc sizes (f64 sincos, fully converged)
+// K4 (count) and K5 (emit).  Slots fall in three populations with very different costs, so each gets its own
+// dense launch instead of diverging inside one kernel:
+//   fast joins  (~75 % of slots: joins inside flattened curves)  thread per slot, a few dozen flops
+//   full joins  (real corners: miter/bevel/round logic, arcs)    compacted list built by the classify pass
+//   End slots   (caps or closing joins, one per sub-path)         list indexed by sub-path (built by K1/K2)
+// count:  k_classify_count -> k_full_count -> k_end_count -> k_scan_offsets (in-place, decoupled look-back)
+// emit:   k_emit_fast -> k_emit_full -> k_emit_end
 // ---------------------------------------------------------------------------------------------------------
 enum { KIND_NONE = 0, KIND_JOIN = 1, KIND_END = 2 };
 struct SlotClass {
@@ -248,24 +262,13 @@ __device__ __forceinline__ SlotClass classify_slot(const Views& w, uint32_t s) {
     return c;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_count_tile(Views w, StrokeParams p, uint8_t* __restrict__ jcode, uint32_t* ticket,
-                                                      uint64_t* desc_v, uint64_t* desc_t, Totals* totals) {
-    __shared__ uint32_t s_warp[WARPS + 1];
-    __shared__ uint32_t s_tile, s_nfull, s_nend;
-    __shared__ unsigned long long s_base_v, s_base_t;
-    __shared__ uint32_t s_nv[BLOCK], s_nt[BLOCK];
-    __shared__ uint8_t s_code[BLOCK];
-    __shared__ uint16_t s_full[BLOCK], s_end[BLOCK];
-    if (threadIdx.x == 0) {
-        s_tile = atomicAdd(ticket, 1u);
-        s_nfull = 0u;
-        s_nend = 0u;
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t s = tile * BLOCK + threadIdx.x;
+// counts of fast joins are written directly; full joins are appended to `full_list` (warp-aggregated atomics).
+__global__ void __launch_bounds__(BLOCK) k_classify_count(Views w, StrokeParams p, uint8_t* __restrict__ jcode,
+                                                          uint32_t* __restrict__ full_list, uint32_t* full_count) {
+    const uint32_t s = blockIdx.x * BLOCK + threadIdx.x;
     uint32_t nv = 0u, nt = 0u;
     uint8_t code = 0;
+    bool is_full = false;
     SlotClass c = classify_slot(w, s);
     if (c.kind == KIND_JOIN) {
         if (join_is_fast(w.pos[c.pk], w.pos[s], w.pos[c.nk], (c.sf & SEG_FS_BIT) != 0u)) {
@@ -273,52 +276,88 @@ __global__ void __launch_bounds__(BLOCK) k_count_tile(Views w, StrokeParams p, u
             nt = (w.segfs[c.pk] & SEG_BEGIN_BIT) ? 0u : 2u;
             code = JC_FAST | JC_SINGLE_POS | JC_SINGLE_NEG;
         } else {
-            s_full[atomicAdd(&s_nfull, 1u)] = (uint16_t)threadIdx.x;
+            is_full = true;
         }
-    } else if (c.kind == KIND_END) {
-        s_end[atomicAdd(&s_nend, 1u)] = (uint16_t)threadIdx.x;
     }
-    s_nv[threadIdx.x] = nv;
-    s_nt[threadIdx.x] = nt;
-    s_code[threadIdx.x] = code;
-    __syncthreads();
-    if (threadIdx.x < s_nfull) {  // dense: full joins
-        const uint32_t lt = s_full[threadIdx.x];
-        const uint32_t s2 = tile * BLOCK + lt;
-        SlotClass c2 = classify_slot(w, s2);
+    if (s < w.n_slots) {
+        w.voff[s] = nv;
+        w.toff[s] = nt;
+        jcode[s] = code;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, is_full);
+    if (mask) {
+        const unsigned lane = threadIdx.x & 31u;
+        uint32_t base = 0u;
+        if (lane == (unsigned)(__ffs((int)mask) - 1)) base = atomicAdd(full_count, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, __ffs((int)mask) - 1);
+        if (is_full) full_list[base + __popc(mask & ((1u << lane) - 1u))] = s;
+    }
+}
+__global__ void __launch_bounds__(128) k_full_count(Views w, StrokeParams p, uint8_t* __restrict__ jcode,
+                                                    const uint32_t* __restrict__ full_list, const uint32_t* full_count) {
+    const uint32_t n = *full_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = full_list[i];
+        const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
         Join j;
-        stream_join(w, p, s2, c2.pk, c2.nk, j);
+        stream_join(w, p, s, pk, nk, j);
         CountSink sink;
         sink.nv = sink.nt = 0u;
         sink.base = 0u;
         VertexTemplate vt;
-        vt.position_on_path = w.pos[s2];
+        vt.position_on_path = w.pos[s];
         vt.half_width = p.half_width;
         vt.advancement = 0.0f;
         vt.src = 0u;
         vt.t = 1.0f;
         emit_join_vertices(sink, vt, j);
-        if (!(w.segfs[c2.pk] & SEG_BEGIN_BIT)) sink.nt += 2u;  // add_edge_triangles: always two for a fixed width
+        if (!(w.segfs[pk] & SEG_BEGIN_BIT)) sink.nt += 2u;  // add_edge_triangles: always two for a fixed width
         tessellate_join(sink, vt, j, p);
-        s_nv[lt] = sink.nv;
-        s_nt[lt] = sink.nt;
-        s_code[lt] = join_encode(j);
+        w.voff[s] = sink.nv;
+        w.toff[s] = sink.nt;
+        jcode[s] = join_encode(j);
     }
-    if (threadIdx.x >= BLOCK - s_nend) {  // End slots on the last threads so that both lists run concurrently
-        const uint32_t lt = s_end[BLOCK - 1u - threadIdx.x];
-        CountSink sink;
-        sink.nv = sink.nt = 0u;
-        sink.base = 0u;
-        stroke_end_slot(w, p, tile * BLOCK + lt, 0u, sink);
-        s_nv[lt] = sink.nv;
-        s_nt[lt] = sink.nt;
-    }
+}
+__global__ void __launch_bounds__(128) k_end_count(Views w, StrokeParams p, const uint32_t* __restrict__ sp_end_slot,
+                                                   uint32_t n_subpaths) {
+    const uint32_t sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp >= n_subpaths) return;
+    const uint32_t s = sp_end_slot[sp];
+    CountSink sink;
+    sink.nv = sink.nt = 0u;
+    sink.base = 0u;
+    stroke_end_slot(w, p, s, 0u, sink);
+    w.voff[s] = sink.nv;
+    w.toff[s] = sink.nt;
+}
+// In-place exclusive scan of the per-slot counts in voff / toff (4 slots per thread).
+constexpr int SCAN_ITEMS = 4;
+__global__ void __launch_bounds__(BLOCK) k_scan_offsets(Views w, uint32_t* ticket, uint64_t* desc_v, uint64_t* desc_t,
+                                                        Totals* totals) {
+    __shared__ uint32_t s_warp[WARPS + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base_v, s_base_t;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
-    nv = s_nv[threadIdx.x];
-    nt = s_nt[threadIdx.x];
+    const uint32_t tile = s_tile;
+    const uint32_t s0 = (tile * BLOCK + threadIdx.x) * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], t[SCAN_ITEMS];
+    if (s0 + SCAN_ITEMS <= w.n_slots) {  // buffers are 16-byte aligned and s0 is a multiple of 4
+        const uint4 a = *reinterpret_cast<const uint4*>(w.voff + s0);
+        const uint4 b = *reinterpret_cast<const uint4*>(w.toff + s0);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (s0 + k < w.n_slots) ? w.voff[s0 + k] : 0u;
+            t[k] = (s0 + k < w.n_slots) ? w.toff[s0 + k] : 0u;
+        }
+    }
+    const uint32_t sum_v = v[0] + v[1] + v[2] + v[3], sum_t = t[0] + t[1] + t[2] + t[3];
     uint32_t agg_v, agg_t;
-    const uint32_t lv = block_exclusive_scan(nv, s_warp, &agg_v);
-    const uint32_t lt_ = block_exclusive_scan(nt, s_warp, &agg_t);
+    uint32_t lv = block_exclusive_scan(sum_v, s_warp, &agg_v);
+    uint32_t lt = block_exclusive_scan(sum_t, s_warp, &agg_t);
     if (threadIdx.x < 32) {
         uint64_t ev = lookback_exclusive(desc_v, tile, agg_v);
         uint64_t et = lookback_exclusive(desc_t, tile, agg_t);
@@ -328,174 +367,102 @@ __global__ void __launch_bounds__(BLOCK) k_count_tile(Views w, StrokeParams p, u
         }
     }
     __syncthreads();
-    if (s < w.n_slots) {
-        w.voff[s] = (uint32_t)(s_base_v + lv);
-        w.toff[s] = (uint32_t)(s_base_t + lt_);
-        jcode[s] = s_code[threadIdx.x];
+    unsigned long long bv = s_base_v + lv, bt = s_base_t + lt;
+    uint32_t ov[SCAN_ITEMS], ot[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        ov[k] = (uint32_t)bv;
+        ot[k] = (uint32_t)bt;
+        bv += v[k];
+        bt += t[k];
     }
-    if (s == w.n_slots - 1u) {
-        const unsigned long long tv = s_base_v + lv + nv, tt = s_base_t + lt_ + nt;
-        w.voff[w.n_slots] = (uint32_t)tv;
-        w.toff[w.n_slots] = (uint32_t)tt;
-        totals->vertices = tv;
-        totals->triangles = tt;
+    if (s0 + SCAN_ITEMS <= w.n_slots) {
+        *reinterpret_cast<uint4*>(w.voff + s0) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<uint4*>(w.toff + s0) = make_uint4(ot[0], ot[1], ot[2], ot[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (s0 + k < w.n_slots) {
+                w.voff[s0 + k] = ov[k];
+                w.toff[s0 + k] = ot[k];
+            }
+    }
+    if (s0 < w.n_slots && s0 + SCAN_ITEMS >= w.n_slots) {  // the thread owning the last slot
+        w.voff[w.n_slots] = (uint32_t)bv;
+        w.toff[w.n_slots] = (uint32_t)bt;
+        totals->vertices = bv;
+        totals->triangles = bt;
     }
 }
 
 // ---- emit ---------------------------------------------------------------------------------------------------
-constexpr uint32_t ARC_CAP = 640;
-struct ArcDesc {
-    float a0, a1;
-    uint32_t va, vb;
-    uint32_t total_neg;  // bit 31: Side::Negative, bits 0..30: number of vertices (2^k - 1)
-    uint32_t first_id;   // global vertex id of the arc's first vertex
-    uint32_t out_v;      // index of that vertex in the vertex array
-    uint32_t out_t;      // index of its triangle in the triangle array
-    VertexTemplate vt;
-};
-struct TileEmitSink : EmitSink {
-    ArcDesc* arcs;
-    uint32_t* n_arcs;
-    GpuVertex* vertices;
-    uint32_t* indices;
-    __device__ __forceinline__ void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb,
-                                        uint32_t total) {
-        const uint32_t slot = atomicAdd(n_arcs, 1u);
-        if (slot < ARC_CAP) {
-            ArcDesc& d = arcs[slot];
-            d.a0 = a0;
-            d.a1 = a1;
-            d.va = va;
-            d.vb = vb;
-            d.total_neg = total | (negative ? 0x80000000u : 0u);
-            d.first_id = base + nv;
-            d.out_v = (uint32_t)((vtx + nv) - vertices);
-            d.out_t = (uint32_t)(((idx + 3ull * nt) - indices) / 3ull);
-            d.vt = vt;
-            nv += total;
-            nt += total;
-        } else {
-            EmitSink::arc(vt, negative, a0, a1, va, vb, total);  // list full: produce the arc inline
-        }
-    }
-};
-
-__global__ void __launch_bounds__(BLOCK) k_emit_tile(Views w, StrokeParams p, const uint8_t* __restrict__ jcode,
+__global__ void __launch_bounds__(BLOCK) k_emit_fast(Views w, StrokeParams p, const uint8_t* __restrict__ jcode,
                                                      GpuVertex* __restrict__ vertices, uint32_t* __restrict__ indices,
                                                      uint32_t vertex_base, Totals* totals) {
-    __shared__ uint32_t s_warp[WARPS + 1];
-    __shared__ uint32_t s_nfull, s_nend, s_narcs;
-    __shared__ uint16_t s_full[BLOCK], s_end[BLOCK];
-    __shared__ ArcDesc s_arcs[ARC_CAP];
-    __shared__ uint32_t s_arc_prefix[ARC_CAP + 1];
-    if (threadIdx.x == 0) {
-        s_nfull = 0u;
-        s_nend = 0u;
-        s_narcs = 0u;
+    const uint32_t s = blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= w.n_slots) return;
+    if (!(jcode[s] & JC_FAST)) return;
+    const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
+    const V2 pp = w.pos[pk], pj = w.pos[s], pn = w.pos[nk];
+    const uint32_t vo = w.voff[s], to = w.toff[s];
+    const V2 normal = fast_join_normal(pp, pj, pn);
+    VertexTemplate vt = slot_vertex_template(w, p, s);
+    EmitSink sink;
+    sink.vtx = vertices + vo;
+    sink.idx = indices + 3ull * to;
+    sink.nv = sink.nt = 0u;
+    sink.base = vertex_base + vo;
+    Join j;
+    j.fast = true;
+    j.fold[0] = j.fold[1] = false;
+    j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, normal, false);
+    j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, -normal, true);
+    if (!(w.segfs[pk] & SEG_BEGIN_BIT)) {
+        Join jp;
+        join_decode_ids(jp, jcode[pk], vertex_base + w.voff[pk]);
+        add_edge_triangles(sink, jp, j);
     }
-    __syncthreads();
-    const uint32_t tile = blockIdx.x;
-    const uint32_t s = tile * BLOCK + threadIdx.x;
-    bool bad = false;
-    SlotClass c = classify_slot(w, s);
-    if (c.kind == KIND_JOIN) {
-        const V2 pp = w.pos[c.pk], pj = w.pos[s], pn = w.pos[c.nk];
-        if (join_is_fast(pp, pj, pn, (c.sf & SEG_FS_BIT) != 0u)) {
-            const uint32_t vo = w.voff[s], to = w.toff[s];
-            const V2 normal = fast_join_normal(pp, pj, pn);
-            VertexTemplate vt = slot_vertex_template(w, p, s);
-            EmitSink sink;
-            sink.vtx = vertices + vo;
-            sink.idx = indices + 3ull * to;
-            sink.nv = sink.nt = 0u;
-            sink.base = vertex_base + vo;
-            Join j;
-            j.fast = true;
-            j.fold[0] = j.fold[1] = false;
-            j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, normal, false);
-            j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, -normal, true);
-            if (!(w.segfs[c.pk] & SEG_BEGIN_BIT)) {
-                Join jp;
-                join_decode_ids(jp, jcode[c.pk], vertex_base + w.voff[c.pk]);
-                add_edge_triangles(sink, jp, j);
-            }
-            bad = (sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to);
-        } else {
-            s_full[atomicAdd(&s_nfull, 1u)] = (uint16_t)threadIdx.x;
-        }
-    } else if (c.kind == KIND_END) {
-        s_end[atomicAdd(&s_nend, 1u)] = (uint16_t)threadIdx.x;
-    }
-    __syncthreads();
-    if (threadIdx.x < s_nfull || threadIdx.x >= BLOCK - s_nend) {
-        const bool is_end = !(threadIdx.x < s_nfull);
-        const uint32_t lt = is_end ? s_end[BLOCK - 1u - threadIdx.x] : s_full[threadIdx.x];
-        const uint32_t s2 = tile * BLOCK + lt;
-        const uint32_t vo = w.voff[s2], to = w.toff[s2];
-        TileEmitSink sink;
+    if ((sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to)) atomicOr(&totals->error, 1u);
+}
+__global__ void __launch_bounds__(128) k_emit_full(Views w, StrokeParams p, const uint8_t* __restrict__ jcode,
+                                                   const uint32_t* __restrict__ full_list, const uint32_t* full_count,
+                                                   GpuVertex* __restrict__ vertices, uint32_t* __restrict__ indices,
+                                                   uint32_t vertex_base, Totals* totals) {
+    const uint32_t n = *full_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = full_list[i];
+        const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
+        const uint32_t vo = w.voff[s], to = w.toff[s];
+        EmitSink sink;
         sink.vtx = vertices + vo;
         sink.idx = indices + 3ull * to;
         sink.nv = sink.nt = 0u;
         sink.base = vertex_base + vo;
-        sink.arcs = s_arcs;
-        sink.n_arcs = &s_narcs;
-        sink.vertices = vertices;
-        sink.indices = indices;
-        if (is_end) {
-            stroke_end_slot(w, p, s2, vertex_base, sink);
-        } else {
-            SlotClass c2 = classify_slot(w, s2);
-            Join j;
-            stream_join(w, p, s2, c2.pk, c2.nk, j);
-            VertexTemplate vt = slot_vertex_template(w, p, s2);
-            emit_join_vertices(sink, vt, j);
-            if (!(w.segfs[c2.pk] & SEG_BEGIN_BIT)) edge_to_previous_join(w, p, s2, c2.pk, vertex_base, jcode, j, sink);
-            tessellate_join(sink, vt, j, p);
-        }
-        bad = bad || (sink.nv != w.voff[s2 + 1] - vo) || (sink.nt != w.toff[s2 + 1] - to);
+        Join j;
+        stream_join(w, p, s, pk, nk, j);
+        VertexTemplate vt = slot_vertex_template(w, p, s);
+        emit_join_vertices(sink, vt, j);
+        if (!(w.segfs[pk] & SEG_BEGIN_BIT)) edge_to_previous_join(w, p, s, pk, vertex_base, jcode, j, sink);
+        tessellate_join(sink, vt, j, p);
+        if ((sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to)) atomicOr(&totals->error, 1u);
     }
-    if (bad) atomicOr(&totals->error, 1u);  // plan/emit divergence: never expected
-    __syncthreads();
-    // ---- phase 3: arc vertices, one thread each ------------------------------------------------------------
-    const uint32_t n_arcs = min(s_narcs, ARC_CAP);
-    if (n_arcs == 0u) return;
-    uint32_t total_arc_vertices;
-    {
-        // prefix over arc sizes: ARC_CAP <= 3 * BLOCK entries, three per thread
-        uint32_t sz[3], sum = 0u;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t a = threadIdx.x * 3u + k;
-            sz[k] = a < n_arcs ? (s_arcs[a].total_neg & 0x7FFFFFFFu) : 0u;
-            sum += sz[k];
-        }
-        uint32_t excl = block_exclusive_scan(sum, s_warp, &total_arc_vertices);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t a = threadIdx.x * 3u + k;
-            if (a <= ARC_CAP) s_arc_prefix[a] = excl;
-            excl += sz[k];
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < total_arc_vertices; i += BLOCK) {
-        uint32_t lo = 0u, hi = n_arcs;  // last arc with prefix <= i
-        while (hi - lo > 1u) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_arc_prefix[mid] <= i) lo = mid; else hi = mid;
-        }
-        const ArcDesc& d = s_arcs[lo];
-        const uint32_t j = i - s_arc_prefix[lo];
-        const uint32_t total = d.total_neg & 0x7FFFFFFFu;
-        const ArcNode n = arc_node(d.a0, d.a1, d.va, d.vb, total, d.first_id, j);
-        EmitSink sink;
-        sink.vtx = vertices + d.out_v + j;
-        sink.idx = indices + 3ull * (d.out_t + j);
-        sink.nv = sink.nt = 0u;
-        sink.base = 0u;
-        sink.add_vertex(d.vt, arc_normal(n.mid), (d.total_neg & 0x80000000u) != 0u);
-        sink.add_triangle(n.ida, n.id, n.idb);
-    }
+}
+__global__ void __launch_bounds__(128) k_emit_end(Views w, StrokeParams p, const uint32_t* __restrict__ sp_end_slot,
+                                                  uint32_t n_subpaths, GpuVertex* __restrict__ vertices,
+                                                  uint32_t* __restrict__ indices, uint32_t vertex_base, Totals* totals) {
+    const uint32_t sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp >= n_subpaths) return;
+    const uint32_t s = sp_end_slot[sp];
+    const uint32_t vo = w.voff[s], to = w.toff[s];
+    const uint32_t nv = w.voff[s + 1] - vo, nt = w.toff[s + 1] - to;
+    if ((nv | nt) == 0u) return;
+    EmitSink sink;
+    sink.vtx = vertices + vo;
+    sink.idx = indices + 3ull * to;
+    sink.nv = sink.nt = 0u;
+    sink.base = vertex_base + vo;
+    stroke_end_slot(w, p, s, vertex_base, sink);
+    if (sink.nv != nv || sink.nt != nt) atomicOr(&totals->error, 1u);
 }
 
 __global__ void __launch_bounds__(128) k_path_ranges(Views w, const uint32_t* __restrict__ path_verb_begin, uint32_t n_paths,
@@ -610,7 +577,9 @@ struct lyon_cuda_ctx {
     std::string err;
     uint64_t launches = 0;
     // workspace
-    DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, jcode, desc, misc;
+    DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, jcode, full_list, sp_end_slot, desc, misc;
+    uint32_t n_subpaths = 0;
+    unsigned persistent_blocks = 148 * 8;
     Totals* h_totals = nullptr;  // pinned
     // state of the last plan
     bool planned = false;
@@ -735,6 +704,10 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     lyon_cuda_ctx* c = new lyon_cuda_ctx();
     c->device = device;
     c->stream = (cudaStream_t)stream;  // NULL is CUDA's default stream
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->persistent_blocks = (unsigned)prop.multiProcessorCount * 8u;
+    }
     if (cudaMallocHost((void**)&c->h_totals, sizeof(Totals)) != cudaSuccess) {
         delete c;
         return LYON_ERR_CUDA;
@@ -748,7 +721,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
-                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->desc, &c->misc};
+                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -818,7 +791,7 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     TRY(ensure(c, c->seg_id, nv1 * 4));
     TRY(ensure(c, c->misc, 512));
     const unsigned vtiles = grid_for(b->n_verbs, BLOCK);
-    TRY(ensure(c, c->desc, (size_t)vtiles * 16));
+    TRY(ensure(c, c->desc, (size_t)vtiles * 24));
     w.verbs = b->verbs;
     w.points = reinterpret_cast<const V2*>(b->points);
     w.seg_pt = (uint32_t*)c->seg_pt.p;
@@ -826,9 +799,10 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     w.seg_tsplit = (float*)c->seg_tsplit.p;
     w.seg_id = (uint32_t*)c->seg_id.p;
     CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
-    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)vtiles * 16, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)vtiles * 24, c->stream));
     k_seg_setup<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params, d_ticket(c, 0), (uint64_t*)c->desc.p,
-                                                (uint64_t*)c->desc.p + vtiles, d_totals(c));
+                                                (uint64_t*)c->desc.p + vtiles, (uint64_t*)c->desc.p + 2 * (size_t)vtiles,
+                                                d_totals(c));
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     TRY(fetch_totals(c));
@@ -848,7 +822,10 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     TRY(ensure(c, c->voff, ns1 * 4));
     TRY(ensure(c, c->toff, ns1 * 4));
     TRY(ensure(c, c->jcode, ns1));
-    const unsigned stiles = grid_for(n_slots, BLOCK);
+    TRY(ensure(c, c->full_list, ns1 * 4));  // worst case: every slot is a full join
+    c->n_subpaths = (uint32_t)c->h_totals->subpaths;
+    TRY(ensure(c, c->sp_end_slot, ((size_t)c->n_subpaths + 1) * 4));
+    const unsigned stiles = grid_for(n_slots, BLOCK * SCAN_ITEMS);
     TRY(ensure(c, c->desc, (size_t)stiles * 16));
     w.pos = (V2*)c->pos.p;
     w.t = (float*)c->t.p;
@@ -857,12 +834,19 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     w.adv = (float*)c->adv.p;
     w.voff = (uint32_t*)c->voff.p;
     w.toff = (uint32_t*)c->toff.p;
-    k_point_gen<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params);
+    uint32_t* sp_end = (uint32_t*)c->sp_end_slot.p;
+    uint32_t* full_list = (uint32_t*)c->full_list.p;
+    uint32_t* full_count = d_ticket(c, 2);
+    k_point_gen<<<vtiles, BLOCK, 0, c->stream>>>(w, c->params, sp_end);
     k_path_walk<<<grid_for(b->n_paths, 128), 128, 0, c->stream>>>(w, c->params, b->path_verb_begin, b->n_paths);
+    k_classify_count<<<grid_for(n_slots, BLOCK), BLOCK, 0, c->stream>>>(w, c->params, (uint8_t*)c->jcode.p, full_list, full_count);
+    k_full_count<<<c->persistent_blocks, 128, 0, c->stream>>>(w, c->params, (uint8_t*)c->jcode.p, full_list, full_count);
+    if (c->n_subpaths)
+        k_end_count<<<grid_for(c->n_subpaths, 128), 128, 0, c->stream>>>(w, c->params, sp_end, c->n_subpaths);
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)stiles * 16, c->stream));
-    k_count_tile<<<stiles, BLOCK, 0, c->stream>>>(w, c->params, (uint8_t*)c->jcode.p, d_ticket(c, 1), (uint64_t*)c->desc.p,
-                                                 (uint64_t*)c->desc.p + stiles, d_totals(c));
-    c->launches += 3;
+    k_scan_offsets<<<stiles, BLOCK, 0, c->stream>>>(w, d_ticket(c, 1), (uint64_t*)c->desc.p, (uint64_t*)c->desc.p + stiles,
+                                                   d_totals(c));
+    c->launches += c->n_subpaths ? 6 : 5;
     CU_TRY(c, cudaGetLastError());
     TRY(fetch_totals(c));
     c->n_vertices = c->h_totals->vertices;
@@ -891,9 +875,18 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
         return LYON_OK;
     }
     if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
-    k_emit_tile<<<grid_for(c->views.n_slots, BLOCK), BLOCK, 0, c->stream>>>(
+    k_emit_fast<<<grid_for(c->views.n_slots, BLOCK), BLOCK, 0, c->stream>>>(
         c->views, c->params, (const uint8_t*)c->jcode.p, (GpuVertex*)d_vertices, d_indices, (uint32_t)vertex_base, d_totals(c));
-    c->launches++;
+    k_emit_full<<<c->persistent_blocks, 128, 0, c->stream>>>(c->views, c->params, (const uint8_t*)c->jcode.p,
+                                                             (const uint32_t*)c->full_list.p, d_ticket(c, 2), (GpuVertex*)d_vertices,
+                                                             d_indices, (uint32_t)vertex_base, d_totals(c));
+    c->launches += 2;
+    if (c->n_subpaths) {
+        k_emit_end<<<grid_for(c->n_subpaths, 128), 128, 0, c->stream>>>(c->views, c->params, (const uint32_t*)c->sp_end_slot.p,
+                                                                         c->n_subpaths, (GpuVertex*)d_vertices, d_indices,
+                                                                         (uint32_t)vertex_base, d_totals(c));
+        c->launches++;
+    }
     if (d_path_vertex_end || d_path_index_end) {
         k_path_ranges<<<grid_for(c->n_paths, 128), 128, 0, c->stream>>>(c->views, c->d_path_verb_begin, c->n_paths,
                                                                        (unsigned long long*)d_path_vertex_end,
