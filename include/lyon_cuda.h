@@ -30,7 +30,8 @@ typedef enum {
     LYON_ERR_INTERNAL = -3,              /* TessellationError::Internal */
     LYON_ERR_CUDA = -4,                  /* CUDA runtime failure (no reference analogue) */
     LYON_ERR_INVALID_ARGUMENT = -5,
-    LYON_ERR_OUT_OF_MEMORY = -6
+    LYON_ERR_OUT_OF_MEMORY = -6,
+    LYON_ERR_BUFFER_TOO_SMALL = -7       /* lyon_cuda_stroke_fused: output capacity exceeded; required sizes returned */
 } lyon_status;
 
 /* Path verbs, the encoding of lyon_path's private `Verb` (crates/path/src/path.rs:29-36). */
@@ -122,6 +123,22 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, co
  * index count of the batch up to and including that path (u64, relative to this batch). */
 int lyon_cuda_stroke_emit(lyon_cuda_ctx* ctx, lyon_stroke_vertex* d_vertices, uint32_t* d_indices,
                           uint64_t vertex_base, uint64_t* d_path_vertex_end, uint64_t* d_path_index_end);
+
+/* Single pass: count, scan and emit fused in one kernel (decoupled look-back assigns every tile of paths its
+ * output base while the tile is still in shared memory), for callers that keep output buffers around like
+ * bench/tess keeps its VertexBuffers (bench/tess/src/main.rs:186-196).  Capacities are in vertices / in u32
+ * indices.  *n_vertices / *n_indices always receive the exact sizes of the result; when a capacity is too small
+ * nothing useful is written and LYON_ERR_BUFFER_TOO_SMALL is returned (grow the buffers and call again).
+ * Needs d_batch->path_point_begin.  Batches holding a path too long for a shared-memory tile (> ~3000 flattened
+ * points) run the two-pass plan/emit pipeline inside this call. */
+int lyon_cuda_stroke_fused(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, const lyon_stroke_options* options,
+                           lyon_stroke_vertex* d_vertices, uint64_t vertex_capacity, uint32_t* d_indices,
+                           uint64_t index_capacity, uint64_t vertex_base, uint64_t* d_path_vertex_end,
+                           uint64_t* d_path_index_end, uint64_t* n_vertices, uint64_t* n_indices);
+
+/* Pipeline selection for plan/emit/fused: 0 = automatic (shared-memory tile pipeline whenever every path of the
+ * batch fits a tile), 1 = always the general multi-kernel pipeline (any path length).  Results are identical. */
+int lyon_cuda_set_pipeline(lyon_cuda_ctx* ctx, int pipeline);
 
 /* Synchronises and reads back the device-side consistency flag of the last emit: LYON_ERR_INTERNAL if the
  * emit pass ever produced a different number of vertices/triangles for a slot than the count pass planned. */

@@ -18,6 +18,7 @@ ERR_INTERNAL = -3
 ERR_CUDA = -4
 ERR_INVALID_ARGUMENT = -5
 ERR_OUT_OF_MEMORY = -6
+ERR_BUFFER_TOO_SMALL = -7
 
 # every symbol include/lyon_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -25,7 +26,7 @@ SYMBOLS = [
     "lyon_cuda_launch_count", "lyon_cuda_workspace_bytes",
     "lyon_cuda_flatten_cubics_count", "lyon_cuda_flatten_cubics_emit",
     "lyon_cuda_flatten_quadratics_count", "lyon_cuda_flatten_quadratics_emit",
-    "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check",
+    "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check", "lyon_cuda_stroke_fused", "lyon_cuda_set_pipeline",
     "lyon_cuda_tessellate_paths", "lyon_cuda_free_host",
 ]
 
@@ -77,6 +78,9 @@ def lib():
     L.lyon_cuda_stroke_plan.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), pu64, pu64]
     L.lyon_cuda_stroke_emit.argtypes = [vp, vp, vp, u64, vp, vp]
     L.lyon_cuda_check.argtypes = [vp]
+    L.lyon_cuda_stroke_fused.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), vp, u64, vp, u64, u64,
+                                         vp, vp, pu64, pu64]
+    L.lyon_cuda_set_pipeline.argtypes = [vp, ctypes.c_int]
     L.lyon_cuda_tessellate_paths.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions),
                                              ctypes.POINTER(vp), pu64, ctypes.POINTER(vp), pu64]
     L.lyon_cuda_free_host.argtypes = [vp]

@@ -79,6 +79,12 @@ LYC_HD float libm_sin(float a) { return (float)sin((double)a); }
 LYC_HD float libm_acos(float a) { return (float)acos((double)a); }
 LYC_HD float libm_asin(float a) { return (float)asin((double)a); }
 LYC_HD float libm_log2(float a) { return (float)log2((double)a); }
+LYC_HD void libm_sincos(float a, float* sn, float* cs) {
+    double s, c;
+    sincos((double)a, &s, &c);
+    *sn = (float)s;
+    *cs = (float)c;
+}
 
 // Rust `as u32` (saturating) and num-traits `to_u32().unwrap_or(1)`
 LYC_HD uint32_t sat_u32(float v) {

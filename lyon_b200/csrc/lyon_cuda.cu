@@ -21,7 +21,7 @@
 #include <string>
 
 #include "../../include/lyon_cuda.h"
-#include "stroke_core.cuh"
+#include "stroke_tile.cuh"
 
 using namespace lyc;
 
@@ -238,30 +238,6 @@ __global__ void __launch_bounds__(128) k_path_walk(Views w, StrokeParams p, cons
 // count:  k_classify_count -> k_full_count -> k_end_count -> k_scan_offsets (in-place, decoupled look-back)
 // emit:   k_emit_fast -> k_emit_full -> k_emit_end
 // ---------------------------------------------------------------------------------------------------------
-enum { KIND_NONE = 0, KIND_JOIN = 1, KIND_END = 2 };
-struct SlotClass {
-    int kind;
-    uint32_t sf, pk, nk;
-};
-__device__ __forceinline__ SlotClass classify_slot(const Views& w, uint32_t s) {
-    SlotClass c;
-    c.kind = KIND_NONE;
-    c.pk = c.nk = 0u;
-    c.sf = 0u;
-    if (s >= w.n_slots) return c;
-    c.sf = w.segfs[s];
-    if (c.sf & SEG_END_BIT) {
-        c.kind = KIND_END;
-        return c;
-    }
-    if ((c.sf & SEG_BEGIN_BIT) || slot_dropped(w, s)) return c;
-    c.nk = next_kept_or_end(w, s);
-    if (w.segfs[c.nk] & SEG_END_BIT) return c;  // last kept point: owned by the End slot
-    c.pk = prev_kept(w, s);
-    c.kind = KIND_JOIN;
-    return c;
-}
-
 // counts of fast joins are written directly; full joins are appended to `full_list` (warp-aggregated atomics).
 __global__ void __launch_bounds__(BLOCK) k_classify_count(Views w, StrokeParams p, uint8_t* __restrict__ jcode,
                                                           uint32_t* __restrict__ full_list, uint32_t* full_count) {
@@ -299,23 +275,12 @@ __global__ void __launch_bounds__(128) k_full_count(Views w, StrokeParams p, uin
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t s = full_list[i];
         const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
-        Join j;
-        stream_join(w, p, s, pk, nk, j);
-        CountSink sink;
-        sink.nv = sink.nt = 0u;
-        sink.base = 0u;
-        VertexTemplate vt;
-        vt.position_on_path = w.pos[s];
-        vt.half_width = p.half_width;
-        vt.advancement = 0.0f;
-        vt.src = 0u;
-        vt.t = 1.0f;
-        emit_join_vertices(sink, vt, j);
-        if (!(w.segfs[pk] & SEG_BEGIN_BIT)) sink.nt += 2u;  // add_edge_triangles: always two for a fixed width
-        tessellate_join(sink, vt, j, p);
-        w.voff[s] = sink.nv;
-        w.toff[s] = sink.nt;
-        jcode[s] = join_encode(j);
+        uint32_t nv, nt;
+        uint8_t code;
+        count_full_join(w, p, s, pk, nk, &nv, &nt, &code);
+        w.voff[s] = nv;
+        w.toff[s] = nt;
+        jcode[s] = code;
     }
 }
 __global__ void __launch_bounds__(128) k_end_count(Views w, StrokeParams p, const uint32_t* __restrict__ sp_end_slot,
@@ -403,25 +368,13 @@ __global__ void __launch_bounds__(BLOCK) k_emit_fast(Views w, StrokeParams p, co
     if (s >= w.n_slots) return;
     if (!(jcode[s] & JC_FAST)) return;
     const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
-    const V2 pp = w.pos[pk], pj = w.pos[s], pn = w.pos[nk];
     const uint32_t vo = w.voff[s], to = w.toff[s];
-    const V2 normal = fast_join_normal(pp, pj, pn);
-    VertexTemplate vt = slot_vertex_template(w, p, s);
     EmitSink sink;
     sink.vtx = vertices + vo;
     sink.idx = indices + 3ull * to;
     sink.nv = sink.nt = 0u;
     sink.base = vertex_base + vo;
-    Join j;
-    j.fast = true;
-    j.fold[0] = j.fold[1] = false;
-    j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, normal, false);
-    j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, -normal, true);
-    if (!(w.segfs[pk] & SEG_BEGIN_BIT)) {
-        Join jp;
-        join_decode_ids(jp, jcode[pk], vertex_base + w.voff[pk]);
-        add_edge_triangles(sink, jp, j);
-    }
+    emit_fast_join(w, p, s, pk, nk, vertex_base, jcode, sink);
     if ((sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to)) atomicOr(&totals->error, 1u);
 }
 __global__ void __launch_bounds__(128) k_emit_full(Views w, StrokeParams p, const uint8_t* __restrict__ jcode,
@@ -438,12 +391,7 @@ __global__ void __launch_bounds__(128) k_emit_full(Views w, StrokeParams p, cons
         sink.idx = indices + 3ull * to;
         sink.nv = sink.nt = 0u;
         sink.base = vertex_base + vo;
-        Join j;
-        stream_join(w, p, s, pk, nk, j);
-        VertexTemplate vt = slot_vertex_template(w, p, s);
-        emit_join_vertices(sink, vt, j);
-        if (!(w.segfs[pk] & SEG_BEGIN_BIT)) edge_to_previous_join(w, p, s, pk, vertex_base, jcode, j, sink);
-        tessellate_join(sink, vt, j, p);
+        emit_full_join(w, p, s, pk, nk, vertex_base, jcode, sink);
         if ((sink.nv != w.voff[s + 1] - vo) || (sink.nt != w.toff[s + 1] - to)) atomicOr(&totals->error, 1u);
     }
 }
@@ -562,6 +510,8 @@ __global__ void __launch_bounds__(BLOCK) k_flat_emit(const float* __restrict__ c
     }
 }
 
+#include "tile_kernels.cuh"
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -580,7 +530,16 @@ struct lyon_cuda_ctx {
     DevBuf seg_pt, seg_off, seg_tsplit, seg_id, pos, t, segfs, len, adv, voff, toff, jcode, full_list, sp_end_slot, desc, misc;
     uint32_t n_subpaths = 0;
     unsigned persistent_blocks = 148 * 8;
+    int num_sms = 148;
+    size_t max_smem_optin = 0;
     Totals* h_totals = nullptr;  // pinned
+    // fused tile pipeline
+    DevBuf path_slots, path_slot_begin, tile_first, tile_desc, tile_base, tile_misc;
+    TileTotals* h_tile_totals = nullptr;  // pinned
+    bool tile_planned = false;            // the last plan went through the tile pipeline
+    lyon_path_batch tile_batch{};
+    uint32_t tile_n_tiles = 0, tile_s_cap = 0, tile_w_v = 0, tile_w_t = 0, tile_quantum = 0;
+    int tile_force_general = 0;  // test hook: lyon_cuda_set_pipeline
     // state of the last plan
     bool planned = false;
     Views views{};
@@ -688,6 +647,144 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
     return LYON_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused tile pipeline, host side
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TILE_NT = 256;
+// tile_misc layout: [0] TileTotals, [256..] tickets (4 x u32)
+TileTotals* d_tile_totals(lyon_cuda_ctx* c) { return reinterpret_cast<TileTotals*>(c->tile_misc.p); }
+uint32_t* d_tile_ticket(lyon_cuda_ctx* c, int i) { return reinterpret_cast<uint32_t*>(static_cast<char*>(c->tile_misc.p) + 256) + i; }
+
+int fetch_tile_totals(lyon_cuda_ctx* c) {
+    CU_TRY(c, cudaMemcpyAsync(c->h_tile_totals, d_tile_totals(c), sizeof(TileTotals), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LYON_OK;
+}
+
+// Tile geometry for a batch whose longest path feeds `max_path` slots.  Returns false when no configuration holds
+// such a path in shared memory (the general multi-kernel pipeline takes the batch instead).
+bool tile_config(const lyon_cuda_ctx* c, uint32_t max_path, uint32_t* s_cap, uint32_t* w_v, uint32_t* w_t, uint32_t* quantum) {
+    static const uint32_t caps[] = {1536u, 3072u, 6144u};
+    static const uint32_t wv[] = {768u, 768u, 384u};
+    for (int i = 0; i < 3; ++i) {
+        if (max_path > caps[i] / 2u) continue;
+        const uint32_t wt = wv[i] * 3u / 2u;
+        if (tile_smem_bytes(caps[i], wv[i], wt) > c->max_smem_optin) continue;
+        *s_cap = caps[i];
+        *w_v = wv[i];
+        *w_t = wt;
+        *quantum = caps[i] - (max_path ? max_path : 1u) + 1u;
+        return true;
+    }
+    return false;
+}
+
+// Pre-pass: per-path slot counts, their scan, the tile table.  *usable = the batch fits the tile pipeline.
+int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
+    *usable = false;
+    if (c->tile_force_general || !b->path_point_begin || b->n_paths == 0 || b->n_verbs == 0) return LYON_OK;
+    const uint32_t np = b->n_paths;
+    TRY(ensure(c, c->path_slots, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->path_slot_begin, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->tile_misc, 512));
+    const unsigned ptiles = grid_for(np, BLOCK * PSCAN_ITEMS);
+    TRY(ensure(c, c->tile_desc, (size_t)ptiles * 8));
+    CU_TRY(c, cudaMemsetAsync(c->tile_misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)ptiles * 8, c->stream));
+    const unsigned warps_needed = np;
+    unsigned blocks = (warps_needed + 7u) / 8u;
+    if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
+    k_path_slots<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
+                                               b->path_point_begin, np, c->params, (uint32_t*)c->path_slots.p, d_tile_totals(c));
+    k_scan_paths<<<ptiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->path_slots.p, np, (unsigned long long*)c->path_slot_begin.p,
+                                                 d_tile_ticket(c, 0), (uint64_t*)c->tile_desc.p, d_tile_totals(c));
+    c->launches += 2;
+    CU_TRY(c, cudaGetLastError());
+    TRY(fetch_tile_totals(c));
+    if (c->h_tile_totals->error & TILE_ERR_POINTS) {
+        c->err = "path_point_begin does not match the points the verbs consume";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    const unsigned long long total = c->h_tile_totals->total_slots;
+    uint32_t s_cap, w_v, w_t, q;
+    if (!tile_config(c, c->h_tile_totals->max_path_slots, &s_cap, &w_v, &w_t, &q)) return LYON_OK;
+    const unsigned long long n_tiles64 = total / q + 1ull;
+    if (n_tiles64 > 0x7FFFFFFFull) return LYON_OK;
+    c->tile_n_tiles = (uint32_t)n_tiles64;
+    c->tile_s_cap = s_cap;
+    c->tile_w_v = w_v;
+    c->tile_w_t = w_t;
+    c->tile_quantum = q;
+    TRY(ensure(c, c->tile_first, ((size_t)c->tile_n_tiles + 1) * 4));
+    TRY(ensure(c, c->tile_desc, (size_t)c->tile_n_tiles * 16));
+    TRY(ensure(c, c->tile_base, (size_t)c->tile_n_tiles * 16));
+    k_tile_bounds<<<grid_for((uint64_t)np + 1, 256), 256, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, q,
+                                                                         c->tile_n_tiles, (uint32_t*)c->tile_first.p);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    c->tile_batch = *b;
+    *usable = true;
+    return LYON_OK;
+}
+
+template <int MODE>
+int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, uint64_t cap_v, uint64_t cap_t, uint64_t vertex_base,
+                uint64_t* d_path_vertex_end, uint64_t* d_path_index_end) {
+    const lyon_path_batch& b = c->tile_batch;
+    TileArgs a{};
+    a.verbs = b.verbs;
+    a.points = reinterpret_cast<const V2*>(b.points);
+    a.path_verb_begin = b.path_verb_begin;
+    a.path_point_begin = b.path_point_begin;
+    a.path_slot_begin = (const unsigned long long*)c->path_slot_begin.p;
+    a.tile_first = (const uint32_t*)c->tile_first.p;
+    a.n_tiles = c->tile_n_tiles;
+    a.n_paths = b.n_paths;
+    a.s_cap = c->tile_s_cap;
+    a.w_v = c->tile_w_v;
+    a.w_t = c->tile_w_t;
+    a.vertices = d_vertices;
+    a.indices = d_indices;
+    a.cap_v = cap_v;
+    a.cap_t = cap_t;
+    a.vertex_base = (uint32_t)vertex_base;
+    a.desc_v = (uint64_t*)c->tile_desc.p;
+    a.desc_t = (uint64_t*)c->tile_desc.p + c->tile_n_tiles;
+    a.tile_base_v = (unsigned long long*)c->tile_base.p;
+    a.tile_base_t = (unsigned long long*)c->tile_base.p + c->tile_n_tiles;
+    a.ticket = d_tile_ticket(c, 1);
+    a.totals = d_tile_totals(c);
+    a.path_vertex_end = (unsigned long long*)d_path_vertex_end;
+    a.path_index_end = (unsigned long long*)d_path_index_end;
+    const size_t smem = tile_smem_bytes(a.s_cap, a.w_v, a.w_t);
+    auto kern = k_stroke_tile<TILE_NT, MODE>;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE_NT, smem));
+    if (per_sm < 1) {
+        c->err = "tile kernel does not fit on an SM";
+        return LYON_ERR_INTERNAL;
+    }
+    unsigned grid = (unsigned)c->num_sms * (unsigned)per_sm;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    CU_TRY(c, cudaMemsetAsync(a.ticket, 0, 4, c->stream));
+    if (MODE != TILE_MODE_EMIT) CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)c->tile_n_tiles * 16, c->stream));
+    kern<<<grid, TILE_NT, smem, c->stream>>>(a, c->params);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
+int tile_error(lyon_cuda_ctx* c) {
+    if (c->h_tile_totals->error) {
+        c->err = (c->h_tile_totals->error & TILE_ERR_EMIT_MISMATCH) ? "internal: emit pass diverged from the count pass"
+                                                                     : "internal: tile pipeline found inconsistent slot counts";
+        return LYON_ERR_INTERNAL;
+    }
+    return LYON_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -706,9 +803,15 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     c->stream = (cudaStream_t)stream;  // NULL is CUDA's default stream
     {
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->persistent_blocks = (unsigned)prop.multiProcessorCount * 8u;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+            c->persistent_blocks = (unsigned)prop.multiProcessorCount * 8u;
+            c->num_sms = prop.multiProcessorCount;
+            c->max_smem_optin = prop.sharedMemPerBlockOptin;
+        }
     }
-    if (cudaMallocHost((void**)&c->h_totals, sizeof(Totals)) != cudaSuccess) {
+    if (cudaMallocHost((void**)&c->h_totals, sizeof(Totals)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_tile_totals, sizeof(TileTotals)) != cudaSuccess) {
+        if (c->h_totals) cudaFreeHost(c->h_totals);
         delete c;
         return LYON_ERR_CUDA;
     }
@@ -721,10 +824,12 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
-                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc};
+                      &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
+                      &c->path_slots, &c->path_slot_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->h_tile_totals) cudaFreeHost(c->h_tile_totals);
     delete c;
 }
 
@@ -784,6 +889,24 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
         return LYON_OK;
     }
     if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
+    c->tile_planned = false;
+    {
+        bool usable = false;
+        TRY(tile_prepass(c, b, &usable));
+        if (usable) {
+            TRY((tile_launch<TILE_MODE_COUNT>(c, nullptr, nullptr, 0, 0, 0, nullptr, nullptr)));
+            TRY(fetch_tile_totals(c));
+            TRY(tile_error(c));
+            c->n_vertices = c->h_tile_totals->vertices;
+            c->n_triangles = c->h_tile_totals->triangles;
+            if (c->n_vertices > 0xFFFFFFFFull || c->n_triangles > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+            *n_vertices = c->n_vertices;
+            *n_indices = 3ull * c->n_triangles;
+            c->tile_planned = true;
+            c->planned = true;
+            return LYON_OK;
+        }
+    }
     const size_t nv1 = (size_t)b->n_verbs + 1;
     TRY(ensure(c, c->seg_pt, nv1 * 4));
     TRY(ensure(c, c->seg_off, nv1 * 4));
@@ -867,6 +990,11 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
     }
     // ids handed out are vertex_base .. vertex_base + V - 1 and must be <= u32::MAX - 1 (geometry_builder.rs:342-346)
     if (c->n_vertices && vertex_base + c->n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (c->tile_planned) {
+        if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+        return tile_launch<TILE_MODE_EMIT>(c, (GpuVertex*)d_vertices, d_indices, c->n_vertices, c->n_triangles, vertex_base,
+                                           d_path_vertex_end, d_path_index_end);
+    }
     if (c->views.n_slots == 0 || c->views.n_verbs == 0) {
         if (c->n_paths) {
             if (d_path_vertex_end) CU_TRY(c, cudaMemsetAsync(d_path_vertex_end, 0, 8ull * c->n_paths, c->stream));
@@ -900,12 +1028,63 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
 // Reads back the device-side consistency flag of the last emit (plan/emit divergence => LYON_ERR_INTERNAL).
 int lyon_cuda_check(lyon_cuda_ctx* c) {
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    if (c->tile_misc.p) {
+        TRY(fetch_tile_totals(c));
+        TRY(tile_error(c));
+    }
     if (!c->misc.p) return LYON_OK;
     TRY(fetch_totals(c));
     if (c->h_totals->error) {
         c->err = "internal: emit pass diverged from the count pass";
         return LYON_ERR_INTERNAL;
     }
+    return LYON_OK;
+}
+
+int lyon_cuda_set_pipeline(lyon_cuda_ctx* c, int pipeline) {
+    if (!c || pipeline < 0 || pipeline > 1) return LYON_ERR_INVALID_ARGUMENT;
+    c->tile_force_general = pipeline == 1;
+    return LYON_OK;
+}
+
+int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, lyon_stroke_vertex* d_vertices,
+                           uint64_t vertex_capacity, uint32_t* d_indices, uint64_t index_capacity, uint64_t vertex_base,
+                           uint64_t* d_path_vertex_end, uint64_t* d_path_index_end, uint64_t* n_vertices, uint64_t* n_indices) {
+    if (!c || !b || !o || !n_vertices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
+    *n_vertices = *n_indices = 0;
+    c->planned = false;
+    c->tile_planned = false;
+    if (o->tolerance != o->tolerance) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN
+    if (o->start_cap > 2 || o->end_cap > 2 || o->line_join > 3) return LYON_ERR_INVALID_ARGUMENT;
+    if (o->variable_line_width >= 0 && b->num_attributes > 0) {
+        c->err = "variable_line_width is not implemented on the device yet";
+        return LYON_ERR_UNSUPPORTED_PARAMETER;
+    }
+    if ((vertex_capacity && !d_vertices) || (index_capacity && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+    bool usable = false;
+    if (b->n_paths && b->n_verbs) {
+        if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
+        c->params = make_params(*o, b->num_attributes);
+        TRY(tile_prepass(c, b, &usable));
+    }
+    if (!usable) {
+        // paths too long for a shared-memory tile (or no path_point_begin): two-pass general pipeline
+        uint64_t nv = 0, ni = 0;
+        TRY(lyon_cuda_stroke_plan(c, b, o, &nv, &ni));
+        *n_vertices = nv;
+        *n_indices = ni;
+        if (nv > vertex_capacity || ni > index_capacity) return LYON_ERR_BUFFER_TOO_SMALL;
+        return lyon_cuda_stroke_emit(c, d_vertices, d_indices, vertex_base, d_path_vertex_end, d_path_index_end);
+    }
+    TRY((tile_launch<TILE_MODE_FUSED>(c, (GpuVertex*)d_vertices, d_indices, vertex_capacity, index_capacity / 3ull, vertex_base,
+                                      d_path_vertex_end, d_path_index_end)));
+    TRY(fetch_tile_totals(c));
+    TRY(tile_error(c));
+    const uint64_t nv = c->h_tile_totals->vertices, nt = c->h_tile_totals->triangles;
+    if (nv > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || (nv && vertex_base + nv - 1ull > 0xFFFFFFFEull)) return LYON_ERR_TOO_MANY_VERTICES;
+    *n_vertices = nv;
+    *n_indices = 3ull * nt;
+    if (c->h_tile_totals->overflow) return LYON_ERR_BUFFER_TOO_SMALL;
     return LYON_OK;
 }
 
@@ -920,20 +1099,23 @@ int lyon_cuda_tessellate_paths(lyon_cuda_ctx* c, const lyon_path_batch* hb, cons
     const size_t a_verbs = ((size_t)hb->n_verbs + 255) & ~(size_t)255;
     const size_t b_points = (size_t)hb->n_points * 8;
     const size_t b_ranges = ((size_t)hb->n_paths + 1) * 4;
+    const size_t a_ranges = (b_ranges + 255) & ~(size_t)255;
     char* d_in = nullptr;
-    CU_TRY(c, cudaMalloc((void**)&d_in, a_verbs + b_points + 256 + b_ranges));
+    CU_TRY(c, cudaMalloc((void**)&d_in, a_verbs + b_points + 256 + 2 * a_ranges));
     lyon_path_batch db = *hb;
     db.verbs = (const uint8_t*)d_in;
     db.points = (const float*)(d_in + a_verbs);
     db.path_verb_begin = (const uint32_t*)(d_in + a_verbs + ((b_points + 255) & ~(size_t)255));
-    db.path_point_begin = nullptr;
+    db.path_point_begin = hb->path_point_begin ? (const uint32_t*)((const char*)db.path_verb_begin + a_ranges) : nullptr;
     int st = LYON_OK;
     void *dv = nullptr, *di = nullptr;
     do {
         if (cudaMemcpyAsync((void*)db.verbs, hb->verbs, hb->n_verbs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
             cudaMemcpyAsync((void*)db.points, hb->points, b_points, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
             cudaMemcpyAsync((void*)db.path_verb_begin, hb->path_verb_begin, b_ranges, cudaMemcpyHostToDevice, c->stream) !=
-                cudaSuccess) {
+                cudaSuccess ||
+            (db.path_point_begin && cudaMemcpyAsync((void*)db.path_point_begin, hb->path_point_begin, b_ranges,
+                                                    cudaMemcpyHostToDevice, c->stream) != cudaSuccess)) {
             st = LYON_ERR_CUDA;
             break;
         }

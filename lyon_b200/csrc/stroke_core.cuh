@@ -66,6 +66,35 @@ struct Views {
     uint32_t* voff;
     uint32_t* toff;
     uint32_t n_slots;
+    // accessors shared with TileViews (the per-item code below is written against these only)
+    LYC_HD V2 P(uint32_t s) const { return pos[s]; }
+    LYC_HD float A(uint32_t s) const { return adv[s]; }
+    LYC_HD float T(uint32_t s) const { return t[s]; }
+    LYC_HD uint32_t F(uint32_t s) const { return segfs[s]; }  // SEG_*_BIT flags in the top bits
+    LYC_HD uint32_t SRC(uint32_t s) const { return seg_id[segfs[s] & SEG_MASK]; }
+    LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
+};
+
+// The same slot arrays for ONE TILE of whole paths held in shared memory by the fused kernel (stroke_tile.cuh):
+// slot indices are tile-relative, flags are one byte (SEG_*_BIT >> 24), the endpoint id is stored per slot.
+static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08;
+struct TileViews {
+    V2* pos;
+    float* t;
+    float* adv;
+    uint32_t* src;   // EndpointId of the slot's vertex source
+    uint8_t* flags;  // TF_*
+    uint32_t* voff;  // aliased by `len` until the count phase
+    uint32_t* toff;
+    uint8_t* jcode;
+    uint32_t n_slots;
+    LYC_HD V2 P(uint32_t s) const { return pos[s]; }
+    LYC_HD float A(uint32_t s) const { return adv[s]; }
+    LYC_HD float T(uint32_t s) const { return t[s]; }
+    LYC_HD uint32_t F(uint32_t s) const { return (uint32_t)flags[s] << 24; }
+    LYC_HD uint32_t SRC(uint32_t s) const { return src[s]; }
+    LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
+    LYC_HD float* len() const { return reinterpret_cast<float*>(voff); }
 };
 
 LYC_HD uint32_t verb_point_count(uint8_t verb, uint32_t a) {
@@ -318,6 +347,8 @@ LYC_HD void path_walk(const Views& w, const StrokeParams& p, uint32_t vb, uint32
 // ---------------------------------------------------------------------------------------------------------
 // Join geometry (fixed line width)
 // ---------------------------------------------------------------------------------------------------------
+// The two sides are indexed [SIDE_POSITIVE] / [SIDE_NEGATIVE]; all indexing below is by compile-time constants
+// (loops over sides are fully unrolled) so the struct lives in registers on the device.
 struct Join {
     bool fast;
     bool fold[2];
@@ -380,16 +411,9 @@ LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const St
     }
     j.line_join = o.line_join;
     j.has_single[0] = j.has_single[1] = false;
-    int front_side;
-    V2 front_normal;
-    if (cross(prev_tangent, next_tangent) >= 0.0f) {
-        front_side = SIDE_NEGATIVE;
-        front_normal = -normal;
-    } else {
-        front_side = SIDE_POSITIVE;
-        front_normal = normal;
-    }
-    int back_side = 1 - front_side;
+    // front side = the outside of the turn (stroke.rs:1665-1669)
+    const bool front_neg = cross(prev_tangent, next_tangent) >= 0.0f;
+    V2 front_normal = front_neg ? -normal : normal;
     V2 extruded_normal = front_normal * hw;
     bool unclipped_miter =
         (j.line_join == JOIN_MITER || j.line_join == JOIN_MITER_CLIP) && !miter_limit_is_exceeded(front_normal, o.miter_limit);
@@ -399,7 +423,8 @@ LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const St
         float d_next = dot(extruded_normal, -next_tangent) - next_length;
         float d_prev = dot(extruded_normal, prev_tangent) - prev_length;
         if (fminf(d_next, d_prev) > 0.0f || sqlen(normal) < 1e-5f) {
-            j.fold[front_side] = true;
+            j.fold[SIDE_NEGATIVE] = front_neg;
+            j.fold[SIDE_POSITIVE] = !front_neg;
             fold = true;
         }
     }
@@ -413,18 +438,23 @@ LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const St
     if (!fold) {
         V2 mp = pj + normal * hw;
         V2 mn = pj - normal * hw;
-        j.has_single[back_side] = true;
-        j.single[back_side] = back_side == SIDE_POSITIVE ? mp : mn;
-        if (unclipped_miter) {
-            j.has_single[front_side] = true;
-            j.single[front_side] = front_side == SIDE_POSITIVE ? mp : mn;
-        } else if (j.line_join == JOIN_MITER_CLIP) {
-            V2 c0 = j.prev[front_side] - pj;
-            V2 c1 = j.next[front_side] - pj;
+        // the back (inner) side always collapses to one vertex; the front side only for an unclipped miter
+        j.has_single[SIDE_POSITIVE] = front_neg || unclipped_miter;
+        j.has_single[SIDE_NEGATIVE] = !front_neg || unclipped_miter;
+        if (j.has_single[SIDE_POSITIVE]) j.single[SIDE_POSITIVE] = mp;
+        if (j.has_single[SIDE_NEGATIVE]) j.single[SIDE_NEGATIVE] = mn;
+        if (!unclipped_miter && j.line_join == JOIN_MITER_CLIP) {
+            V2 c0 = (front_neg ? j.prev[SIDE_NEGATIVE] : j.prev[SIDE_POSITIVE]) - pj;
+            V2 c1 = (front_neg ? j.next[SIDE_NEGATIVE] : j.next[SIDE_POSITIVE]) - pj;
             V2 pn_, nn_;
             get_clip_intersections(c0, c1, front_normal, o.miter_limit * hw, &pn_, &nn_);
-            j.prev[front_side] = pj + pn_;
-            j.next[front_side] = pj + nn_;
+            if (front_neg) {
+                j.prev[SIDE_NEGATIVE] = pj + pn_;
+                j.next[SIDE_NEGATIVE] = pj + nn_;
+            } else {
+                j.prev[SIDE_POSITIVE] = pj + pn_;
+                j.next[SIDE_POSITIVE] = pj + nn_;
+            }
         }
     }
 }
@@ -437,18 +467,13 @@ LYC_HD uint32_t join_assign_ids(Join& j, uint32_t base) {
         j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = base + 1u;
         return 2u;
     }
-    uint32_t n = 0;
-    for (int side = SIDE_NEGATIVE; side >= SIDE_POSITIVE; --side) {
-        if (j.has_single[side]) {
-            j.prev_v[side] = j.next_v[side] = base + n;
-            n += 1u;
-        } else {
-            j.prev_v[side] = base + n;
-            j.next_v[side] = base + n + 1u;
-            n += 2u;
-        }
-    }
-    return n;
+    const uint32_t nneg = j.has_single[SIDE_NEGATIVE] ? 1u : 2u;
+    const uint32_t npos = j.has_single[SIDE_POSITIVE] ? 1u : 2u;
+    j.prev_v[SIDE_NEGATIVE] = base;
+    j.next_v[SIDE_NEGATIVE] = base + nneg - 1u;
+    j.prev_v[SIDE_POSITIVE] = base + nneg;
+    j.next_v[SIDE_POSITIVE] = base + nneg + npos - 1u;
+    return nneg + npos;
 }
 
 // Per-slot join layout code written by the count pass and read back by the emit pass (so that the edge
@@ -520,12 +545,12 @@ LYC_HD ArcNode arc_node(float a0, float a1, uint32_t va, uint32_t vb, uint32_t t
     return n;
 }
 LYC_HD V2 arc_normal(float mid) {  // vector(mid.cos(), mid.sin()), stroke.rs:2627
-    double sn, cs;
-    sincos((double)mid, &sn, &cs);
-    return v2((float)cs, (float)sn);
+    float sn, cs;
+    libm_sincos(mid, &sn, &cs);
+    return v2(cs, sn);
 }
 struct EmitSink {
-    GpuVertex* vtx;  // first vertex owned by this slot
+    GpuVertex* vtx;  // first vertex owned by this slot (global memory, or the shared-memory staging window)
     uint32_t* idx;   // first index owned by this slot
     uint32_t nv, nt, base;
     LYC_HD uint32_t next_id() const { return base + nv; }
@@ -614,21 +639,21 @@ LYC_HD uint32_t arc_subdivisions(float diff, float radius, const StrokeParams& o
     return round_log2_segments(num_segments);
 }
 
-// tessellate_round_join (stroke.rs:1968-2021)
-template <class Sink>
-LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Join& j, int side, const StrokeParams& o) {
+// tessellate_round_join (stroke.rs:1968-2021).  SIDE is a compile-time constant at every call site.
+template <int SIDE, class Sink>
+LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Join& j, const StrokeParams& o) {
     V2 center = vt.position_on_path;
     float radius = vt.half_width;
-    V2 start_normal = j.prev[side] - center;
-    V2 end_normal = j.next[side] - center;
-    uint32_t start_vertex = j.prev_v[side];
-    uint32_t end_vertex = j.next_v[side];
-    float angle_sign = side == SIDE_NEGATIVE ? 1.0f : -1.0f;
+    V2 start_normal = j.prev[SIDE] - center;
+    V2 end_normal = j.next[SIDE] - center;
+    uint32_t start_vertex = j.prev_v[SIDE];
+    uint32_t end_vertex = j.next_v[SIDE];
+    float angle_sign = SIDE == SIDE_NEGATIVE ? 1.0f : -1.0f;
     float start_angle = angle_from_x_axis(start_normal);
     float diff = angle_to(start_angle, angle_from_x_axis(end_normal));
     if (diff * angle_sign < 0.0f) diff = angle_sign * (2.0f * LYC_PI_F - fabsf(diff));
     float end_angle = start_angle + diff;
-    if (side == SIDE_NEGATIVE) {
+    if (SIDE == SIDE_NEGATIVE) {
         float ta = start_angle;
         start_angle = end_angle;
         end_angle = ta;
@@ -637,7 +662,7 @@ LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Jo
         end_vertex = tv;
     }
     uint32_t k = arc_subdivisions(diff, radius, o);
-    emit_arc(sink, vt, side != SIDE_POSITIVE, start_angle, end_angle, start_vertex, end_vertex, k);
+    emit_arc(sink, vt, SIDE != SIDE_POSITIVE, start_angle, end_angle, start_vertex, end_vertex, k);
 }
 
 // tessellate_join (stroke.rs:1907-1965)
@@ -656,8 +681,8 @@ LYC_HD void tessellate_join(Sink& sink, const VertexTemplate& vt, const Join& j,
         }
     }
     if (j.line_join == JOIN_ROUND) {
-        if (need0) tessellate_round_join(sink, vt, j, SIDE_POSITIVE, o);
-        if (need1) tessellate_round_join(sink, vt, j, SIDE_NEGATIVE, o);
+        if (need0) tessellate_round_join<SIDE_POSITIVE>(sink, vt, j, o);
+        if (need1) tessellate_round_join<SIDE_NEGATIVE>(sink, vt, j, o);
     }
 }
 
@@ -671,15 +696,20 @@ LYC_HD void emit_join_vertices(Sink& sink, const VertexTemplate& vt, Join& j) {
         j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = nv;
         return;
     }
-    for (int side = SIDE_NEGATIVE; side >= SIDE_POSITIVE; --side) {  // add_join_base_vertices, stroke.rs:2024-2055
-        bool neg = side == SIDE_NEGATIVE;
-        if (j.has_single[side]) {
-            uint32_t id = sink.add_vertex(vt, (j.single[side] - vt.position_on_path) / vt.half_width, neg);
-            j.prev_v[side] = j.next_v[side] = id;
-        } else {
-            j.prev_v[side] = sink.add_vertex(vt, (j.prev[side] - vt.position_on_path) / vt.half_width, neg);
-            j.next_v[side] = sink.add_vertex(vt, (j.next[side] - vt.position_on_path) / vt.half_width, neg);
-        }
+    // add_join_base_vertices, stroke.rs:2024-2055: Negative side first, then Positive
+    if (j.has_single[SIDE_NEGATIVE]) {
+        uint32_t id = sink.add_vertex(vt, (j.single[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
+        j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = id;
+    } else {
+        j.prev_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (j.prev[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
+        j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (j.next[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
+    }
+    if (j.has_single[SIDE_POSITIVE]) {
+        uint32_t id = sink.add_vertex(vt, (j.single[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
+        j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = id;
+    } else {
+        j.prev_v[SIDE_POSITIVE] = sink.add_vertex(vt, (j.prev[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
+        j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, (j.next[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
     }
 }
 
@@ -704,49 +734,54 @@ LYC_HD void tessellate_round_cap(Sink& sink, VertexTemplate vt, V2 center, float
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Slot neighbourhood helpers
+// Slot neighbourhood helpers (W = Views or TileViews)
 // ---------------------------------------------------------------------------------------------------------
-LYC_HD bool slot_dropped(const Views& w, uint32_t s) { return is_nan(w.adv[s]); }
-LYC_HD uint32_t prev_kept(const Views& w, uint32_t s) {  // s is a kept non-Begin point: a kept predecessor exists
+template <class W>
+LYC_HD bool slot_dropped(const W& w, uint32_t s) { return is_nan(w.A(s)); }
+template <class W>
+LYC_HD uint32_t prev_kept(const W& w, uint32_t s) {  // s is a kept non-Begin point: a kept predecessor exists
     uint32_t j = s - 1u;
     while (slot_dropped(w, j)) --j;
     return j;
 }
-LYC_HD uint32_t next_kept_or_end(const Views& w, uint32_t s) {  // returns the End slot when s is the last kept point
+template <class W>
+LYC_HD uint32_t next_kept_or_end(const W& w, uint32_t s) {  // returns the End slot when s is the last kept point
     uint32_t j = s + 1u;
-    while (!(w.segfs[j] & SEG_END_BIT) && slot_dropped(w, j)) ++j;
+    while (!(w.F(j) & SEG_END_BIT) && slot_dropped(w, j)) ++j;
     return j;
 }
-LYC_HD VertexTemplate slot_vertex_template(const Views& w, const StrokeParams& o, uint32_t s) {
+template <class W>
+LYC_HD VertexTemplate slot_vertex_template(const W& w, const StrokeParams& o, uint32_t s) {
     VertexTemplate vt;
-    vt.position_on_path = w.pos[s];
+    vt.position_on_path = w.P(s);
     vt.half_width = o.half_width;
-    vt.advancement = w.adv[s];
-    vt.src = w.seg_id[w.segfs[s] & SEG_MASK];
-    vt.t = w.t[s];
+    vt.advancement = w.A(s);
+    vt.src = w.SRC(s);
+    vt.t = w.T(s);
     return vt;
 }
 // Join at kept interior point `s` as computed while the stream was running (not by end()).
-LYC_HD void stream_join(const Views& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, Join& j) {
-    compute_join_fw(j, w.pos[pk], w.pos[s], w.pos[nk], (w.segfs[s] & SEG_FS_BIT) != 0u, o);
+template <class W>
+LYC_HD void stream_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, Join& j) {
+    compute_join_fw(j, w.P(pk), w.P(s), w.P(nk), (w.F(s) & SEG_FS_BIT) != 0u, o);
 }
 // Base vertex id of slot s. Counting pass: ids are never compared across slots in a way that matters for
 // fixed width, any distinct bases do.
-template <class Sink>
-LYC_HD uint32_t slot_vertex_base(const Views& w, uint32_t s, uint32_t global_base) {
-    return Sink::kCounting ? (0x40000000u + (s & 0xFFFFFu) * 16u) : (global_base + w.voff[s]);
+template <class Sink, class W>
+LYC_HD uint32_t slot_vertex_base(const W& w, uint32_t s, uint32_t global_base) {
+    return Sink::kCounting ? (0x40000000u + (s & 0xFFFFFu) * 16u) : (global_base + w.VO(s));
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // K4/K5 per slot
 // ---------------------------------------------------------------------------------------------------------
-template <class Sink>
-LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink);
+template <class Sink, class W>
+LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink);
 
 // Edge triangles between the previous stream join (at kept slot pk, not a Begin) and join j at slot s.
 // With a jcode array (emit pass) the previous join's vertex layout is decoded, otherwise it is recomputed.
-template <class Sink>
-LYC_HD void edge_to_previous_join(const Views& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t global_base,
+template <class Sink, class W>
+LYC_HD void edge_to_previous_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t global_base,
                                   const uint8_t* jcode, const Join& j, Sink& sink) {
     Join jp;
     if (jcode) {
@@ -759,24 +794,100 @@ LYC_HD void edge_to_previous_join(const Views& w, const StrokeParams& o, uint32_
     add_edge_triangles(sink, jp, j);
 }
 
-template <class Sink>
-LYC_HD void stroke_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink,
+// Slot classes.  The join at kept point i is owned by slot i; everything end() emits by the End slot.
+enum { KIND_NONE = 0, KIND_JOIN = 1, KIND_END = 2 };
+struct SlotClass {
+    int kind;
+    uint32_t sf, pk, nk;
+};
+template <class W>
+LYC_HD SlotClass classify_slot(const W& w, uint32_t s) {
+    SlotClass c;
+    c.kind = KIND_NONE;
+    c.pk = c.nk = 0u;
+    c.sf = 0u;
+    if (s >= w.n_slots) return c;
+    c.sf = w.F(s);
+    if (c.sf & SEG_END_BIT) {
+        c.kind = KIND_END;
+        return c;
+    }
+    if ((c.sf & SEG_BEGIN_BIT) || slot_dropped(w, s)) return c;
+    c.nk = next_kept_or_end(w, s);
+    if (w.F(c.nk) & SEG_END_BIT) return c;  // last kept point: owned by the End slot
+    c.pk = prev_kept(w, s);
+    c.kind = KIND_JOIN;
+    return c;
+}
+// Count pass of a join that does not take the flattened_step fast path.
+template <class W>
+LYC_HD void count_full_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t* nv,
+                            uint32_t* nt, uint8_t* code) {
+    Join j;
+    stream_join(w, o, s, pk, nk, j);
+    CountSink sink;
+    sink.nv = sink.nt = 0u;
+    sink.base = 0u;
+    VertexTemplate vt;
+    vt.position_on_path = w.P(s);
+    vt.half_width = o.half_width;
+    vt.advancement = 0.0f;
+    vt.src = 0u;
+    vt.t = 1.0f;
+    emit_join_vertices(sink, vt, j);
+    if (!(w.F(pk) & SEG_BEGIN_BIT)) sink.nt += 2u;  // add_edge_triangles: always two for a fixed width
+    tessellate_join(sink, vt, j, o);
+    *nv = sink.nv;
+    *nt = sink.nt;
+    *code = join_encode(j);
+}
+// Emit pass of a fast join (flattened_step, stroke.rs:1743-1806).
+template <class Sink, class W>
+LYC_HD void emit_fast_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t global_base,
+                           const uint8_t* jcode, Sink& sink) {
+    const V2 normal = fast_join_normal(w.P(pk), w.P(s), w.P(nk));
+    VertexTemplate vt = slot_vertex_template(w, o, s);
+    Join j;
+    j.fast = true;
+    j.fold[0] = j.fold[1] = false;
+    j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, normal, false);
+    j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, -normal, true);
+    if (!(w.F(pk) & SEG_BEGIN_BIT)) {
+        Join jp;
+        join_decode_ids(jp, jcode[pk], global_base + w.VO(pk));
+        add_edge_triangles(sink, jp, j);
+    }
+}
+// Emit pass of any other stream join.
+template <class Sink, class W>
+LYC_HD void emit_full_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t global_base,
+                           const uint8_t* jcode, Sink& sink) {
+    Join j;
+    stream_join(w, o, s, pk, nk, j);
+    VertexTemplate vt = slot_vertex_template(w, o, s);
+    emit_join_vertices(sink, vt, j);
+    if (!(w.F(pk) & SEG_BEGIN_BIT)) edge_to_previous_join(w, o, s, pk, global_base, jcode, j, sink);
+    tessellate_join(sink, vt, j, o);
+}
+
+template <class Sink, class W>
+LYC_HD void stroke_slot(const W& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink,
                         const uint8_t* jcode = nullptr, uint8_t* jcode_out = nullptr) {
-    uint32_t sf = w.segfs[s];
+    uint32_t sf = w.F(s);
     if (sf & SEG_END_BIT) {
         stroke_end_slot(w, o, s, global_base, sink);
         return;
     }
     if ((sf & SEG_BEGIN_BIT) || slot_dropped(w, s)) return;
     uint32_t nk = next_kept_or_end(w, s);
-    if (w.segfs[nk] & SEG_END_BIT) return;  // last kept point: owned by the End slot
+    if (w.F(nk) & SEG_END_BIT) return;  // last kept point: owned by the End slot
     uint32_t pk = prev_kept(w, s);
     Join j;
     stream_join(w, o, s, pk, nk, j);
     VertexTemplate vt = slot_vertex_template(w, o, s);
     if (jcode_out) jcode_out[s] = join_encode(j);
     emit_join_vertices(sink, vt, j);
-    if (!(w.segfs[pk] & SEG_BEGIN_BIT))  // count > 2: edge between the previous join and this one (stroke.rs:1611-1613)
+    if (!(w.F(pk) & SEG_BEGIN_BIT))  // count > 2: edge between the previous join and this one (stroke.rs:1611-1613)
         edge_to_previous_join(w, o, s, pk, global_base, jcode, j, sink);
     tessellate_join(sink, vt, j, o);
 }
@@ -812,11 +923,25 @@ LYC_HD void tessellate_empty_cap(Sink& sink, VertexTemplate vt, const StrokePara
     }
 }
 
+// One end of an open sub-path: the side position clipped against the cap line in f64
+// (tessellate_last_edge / tessellate_first_edge, stroke.rs:2160-2180, 2235-2255).
+LYC_HD V2 clip_cap_side(uint8_t cap, V2 end_point, V2 other_point, V2 side_position, V2 towards, float hw) {
+    if (cap == CAP_SQUARE || cap == CAP_BUTT) {
+        float clip = cap == CAP_SQUARE ? hw : 0.0f;
+        V2 normal = normalize(end_point - other_point);
+        LineD clip_line = line_d(end_point + normal * clip, tangent(normal));
+        LineD side_line = line_d(side_position, side_position - towards);
+        V2 inter;
+        if (line_intersection(clip_line, side_line, &inter)) return inter;
+    }
+    return side_position;
+}
+
 // Everything `end()` emits for one sub-path (stroke.rs:1179-1193): end_with_caps (:1322-1378) or close (:1206-1279).
-template <class Sink>
-LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink) {
+template <class Sink, class W>
+LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint32_t global_base, Sink& sink) {
     const float hw = o.half_width;
-    V2 rec = w.pos[s];
+    V2 rec = w.P(s);
     uint32_t b0 = f2u(rec.x);
     uint32_t flags = f2u(rec.y);
     uint32_t m = flags & 3u;
@@ -834,11 +959,11 @@ LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, u
     uint32_t s_l1 = s - 1u;                   // last kept point
     while (slot_dropped(w, s_l1)) --s_l1;
     uint32_t s_l2 = prev_kept(w, s_l1);
-    V2 P0 = w.pos[b0], P1 = w.pos[s_p1];
+    V2 P0 = w.P(b0), P1 = w.P(s_p1);
 
     if (!(close && m > 2u)) {
         // ---- end_with_caps ---------------------------------------------------------------------------------
-        V2 pl2 = w.pos[s_l2], pl1 = w.pos[s_l1];
+        V2 pl2 = w.P(s_l2), pl1 = w.P(s_l1);
         // p0 = second to last point: its `next` side points, vertex ids and fold flags
         Join j0;
         if (m == 2u) {
@@ -862,19 +987,10 @@ LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, u
         VertexTemplate vt = slot_vertex_template(w, o, s_l1);  // advancement = chain value = p0.adv + |v|
         V2 v = pl1 - pl2;
         uint32_t p1_prev_v[2];
-        for (int side = 0; side < 2; ++side) {
-            V2 side_position = p1_prev[side];
-            if (o.end_cap == CAP_SQUARE || o.end_cap == CAP_BUTT) {
-                float clip = o.end_cap == CAP_SQUARE ? hw : 0.0f;
-                V2 normal = normalize(pl1 - pl2);
-                LineD clip_line = line_d(pl1 + normal * clip, tangent(normal));
-                LineD side_line = line_d(side_position, side_position - j0.next[side]);
-                V2 inter;
-                if (!line_intersection(clip_line, side_line, &inter)) inter = p1_prev[side];
-                p1_prev[side] = inter;
-            }
-            p1_prev_v[side] = sink.add_vertex(vt, (p1_prev[side] - pl1) / hw, side != SIDE_POSITIVE);
-        }
+        p1_prev[SIDE_POSITIVE] = clip_cap_side(o.end_cap, pl1, pl2, p1_prev[SIDE_POSITIVE], j0.next[SIDE_POSITIVE], hw);
+        p1_prev_v[SIDE_POSITIVE] = sink.add_vertex(vt, (p1_prev[SIDE_POSITIVE] - pl1) / hw, false);
+        p1_prev[SIDE_NEGATIVE] = clip_cap_side(o.end_cap, pl1, pl2, p1_prev[SIDE_NEGATIVE], j0.next[SIDE_NEGATIVE], hw);
+        p1_prev_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (p1_prev[SIDE_NEGATIVE] - pl1) / hw, true);
         if (m > 2u) add_edge_triangles(sink, j0.prev_v, j0.next_v, j0.fold, p1_prev_v, p1_prev_v, no_fold);
         if (o.end_cap == CAP_ROUND)
             tessellate_round_cap(sink, vt, pl1, hw, p1_prev[SIDE_POSITIVE] - pl1, p1_prev_v[SIDE_POSITIVE],
@@ -886,36 +1002,31 @@ LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, u
         uint32_t second_prev_v[2], second_next_v[2];
         bool second_fold[2] = {false, false};
         if (m == 2u) {
-            for (int side = 0; side < 2; ++side) {
-                second_prev[side] = p1_prev[side];
-                second_prev_v[side] = second_next_v[side] = p1_prev_v[side];
-            }
+            second_prev[0] = p1_prev[0];
+            second_prev[1] = p1_prev[1];
+            second_prev_v[0] = second_next_v[0] = p1_prev_v[0];
+            second_prev_v[1] = second_next_v[1] = p1_prev_v[1];
         } else {
             uint32_t s_p2 = next_kept_or_end(w, s_p1);
             Join j1;
             stream_join(w, o, s_p1, b0, s_p2, j1);
             join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
-            for (int side = 0; side < 2; ++side) {
-                second_prev[side] = j1.prev[side];
-                second_prev_v[side] = j1.prev_v[side];
-                second_next_v[side] = j1.next_v[side];
-                second_fold[side] = j1.fold[side];
-            }
+            second_prev[0] = j1.prev[0];
+            second_prev[1] = j1.prev[1];
+            second_prev_v[0] = j1.prev_v[0];
+            second_prev_v[1] = j1.prev_v[1];
+            second_next_v[0] = j1.next_v[0];
+            second_next_v[1] = j1.next_v[1];
+            second_fold[0] = j1.fold[0];
+            second_fold[1] = j1.fold[1];
         }
         VertexTemplate vf = slot_vertex_template(w, o, b0);
         uint32_t first_next_v[2];
-        for (int side = 0; side < 2; ++side) {
-            V2 side_position = first_next[side];
-            if (o.start_cap == CAP_SQUARE || o.start_cap == CAP_BUTT) {
-                float clip = o.start_cap == CAP_SQUARE ? hw : 0.0f;
-                V2 normal = normalize(P0 - P1);
-                LineD clip_line = line_d(P0 + normal * clip, tangent(normal));
-                LineD side_line = line_d(side_position, side_position - second_prev[side]);
-                V2 inter;
-                if (!line_intersection(clip_line, side_line, &inter)) inter = first_next[side];
-                side_position = inter;
-            }
-            first_next_v[side] = sink.add_vertex(vf, (side_position - P0) / hw, side != SIDE_POSITIVE);
+        {
+            V2 sp = clip_cap_side(o.start_cap, P0, P1, first_next[SIDE_POSITIVE], second_prev[SIDE_POSITIVE], hw);
+            first_next_v[SIDE_POSITIVE] = sink.add_vertex(vf, (sp - P0) / hw, false);
+            V2 sn = clip_cap_side(o.start_cap, P0, P1, first_next[SIDE_NEGATIVE], second_prev[SIDE_NEGATIVE], hw);
+            first_next_v[SIDE_NEGATIVE] = sink.add_vertex(vf, (sn - P0) / hw, true);
         }
         {
             const uint32_t unset[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -933,13 +1044,13 @@ LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, u
     Join j1;  // firsts[1]
     stream_join(w, o, s_p1, b0, s_p2, j1);
     join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
-    const float start_advancement = w.adv[b0];
-    V2 A = w.pos[s_l2], B = w.pos[s_l1];
+    const float start_advancement = w.A(b0);
+    V2 A = w.P(s_l2), B = w.P(s_l1);
     uint32_t s_l3 = prev_kept(w, s_l2);  // exists: m > 2
     Join ja;                             // join at A = second to last kept point (already emitted by its slot)
     stream_join(w, o, s_l2, s_l3, s_l1, ja);
     join_assign_ids(ja, slot_vertex_base<Sink>(w, s_l2, global_base));
-    const bool b_fs = (w.segfs[s_l1] & SEG_FS_BIT) != 0u;
+    const bool b_fs = (w.F(s_l1) & SEG_FS_BIT) != 0u;
 
     bool segment_added = !(sqlen(B - P0) < o.merge_thr);  // step(firsts[0]) merge test (stroke.rs:1531)
     Join jc;       // the join the two extra vertices are re-created on ("p0" at stroke.rs:1248)
@@ -966,16 +1077,18 @@ LYC_HD void stroke_end_slot(const Views& w, const StrokeParams& o, uint32_t s, u
         vc.position_on_path = P0;
         // B's advancement was already fixed iff the join at A took the fast path (flattened_step sets
         // next.advancement, stroke.rs:1765-1769); otherwise it is computed now from the moved position.
-        if (!ja.fast) vc.advancement = w.adv[s_l2] + length(P0 - A);
+        if (!ja.fast) vc.advancement = w.A(s_l2) + length(P0 - A);
         emit_join_vertices(sink, vc, jc);
         add_edge_triangles(sink, ja, jc);
         tessellate_join(sink, vc, jc, o);
     }
     // Re-create the two vertices towards the second endpoint with the sub-path start advancement (stroke.rs:1248-1275)
     vc.advancement = start_advancement;
-    for (int side = 0; side < 2; ++side) {
-        V2 ref = jc.has_single[side] ? jc.single[side] : jc.next[side];
-        jc.next_v[side] = sink.add_vertex(vc, (ref - vc.position_on_path) / vc.half_width, side != SIDE_POSITIVE);
+    {
+        V2 rp = jc.has_single[SIDE_POSITIVE] ? jc.single[SIDE_POSITIVE] : jc.next[SIDE_POSITIVE];
+        jc.next_v[SIDE_POSITIVE] = sink.add_vertex(vc, (rp - vc.position_on_path) / vc.half_width, false);
+        V2 rn = jc.has_single[SIDE_NEGATIVE] ? jc.single[SIDE_NEGATIVE] : jc.next[SIDE_NEGATIVE];
+        jc.next_v[SIDE_NEGATIVE] = sink.add_vertex(vc, (rn - vc.position_on_path) / vc.half_width, true);
     }
     add_edge_triangles(sink, jc, j1);
 }

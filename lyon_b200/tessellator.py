@@ -25,7 +25,7 @@ def _raise(L, ctx, code: int):
     msg = L.lyon_cuda_last_error(ctx)
     msg = msg.decode() if msg else ""
     names = {-1: "UnsupportedParameter", -2: "TooManyVertices", -3: "Internal", -4: "CudaError",
-             -5: "InvalidArgument", -6: "OutOfMemory"}
+             -5: "InvalidArgument", -6: "OutOfMemory", -7: "BufferTooSmall"}
     what = f"{names.get(code, 'Error')}: {msg}" if msg else names.get(code, "Error")
     if code == _ffi.ERR_TOO_MANY_VERTICES:
         raise TooManyVertices(code, what)
@@ -129,6 +129,49 @@ class DeviceTessellator:
         if with_ranges:
             return vertices, indices, pve, pie
         return vertices, indices
+
+    def stroke_fused(self, dbatch: DeviceBatch, options: StrokeOptions, vertices=None, indices=None, vertex_base: int = 0,
+                     with_ranges: bool = False):
+        """Single-pass stroke (lyon_cuda_stroke_fused): count, scan and emit in one kernel, into caller-kept
+        device buffers -- `vertices` float32 [capV, 8], `indices` int32 [capI].  Without buffers the tessellator
+        keeps its own grow-only pair (the way bench/tess keeps one VertexBuffers across iterations); a call whose
+        result does not fit grows them and runs once more.  Returns views (vertices[:nv], indices[:ni])."""
+        torch = self.torch
+        own = vertices is None or indices is None
+        if own:
+            vertices, indices = getattr(self, "_own_v", None), getattr(self, "_own_i", None)
+            if vertices is None:
+                vertices = self._own_v = torch.empty((0, 8), dtype=torch.float32, device=self.device)
+                indices = self._own_i = torch.empty((0,), dtype=torch.int32, device=self.device)
+        pve = pie = None
+        if with_ranges:
+            pve = torch.empty((dbatch.n_paths,), dtype=torch.int64, device=self.device)
+            pie = torch.empty((dbatch.n_paths,), dtype=torch.int64, device=self.device)
+        nv, ni = ctypes.c_uint64(), ctypes.c_uint64()
+        cb, co = dbatch.c_struct(), options.to_c()
+        for attempt in range(2):
+            st = self.L.lyon_cuda_stroke_fused(self.ctx, ctypes.byref(cb), ctypes.byref(co), vertices.data_ptr(),
+                                               vertices.shape[0], indices.data_ptr(), indices.shape[0], vertex_base,
+                                               pve.data_ptr() if with_ranges else None,
+                                               pie.data_ptr() if with_ranges else None, ctypes.byref(nv), ctypes.byref(ni))
+            if st == _ffi.ERR_BUFFER_TOO_SMALL and own and attempt == 0:
+                del vertices, indices
+                self._own_v = self._own_i = None
+                vertices = self._own_v = torch.empty((nv.value + nv.value // 64 + 64, 8), dtype=torch.float32, device=self.device)
+                indices = self._own_i = torch.empty((ni.value + ni.value // 64 + 256,), dtype=torch.int32, device=self.device)
+                continue
+            break
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        out = (vertices[:nv.value], indices[:ni.value])
+        return out + (pve, pie) if with_ranges else out
+
+    def set_pipeline(self, general: bool):
+        """False: automatic (fused shared-memory tile pipeline when every path fits a tile); True: always the
+        general multi-kernel pipeline.  Both produce identical output."""
+        st = self.L.lyon_cuda_set_pipeline(self.ctx, 1 if general else 0)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
 
     def check(self):
         st = self.L.lyon_cuda_check(self.ctx)

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/lyon_cuda.h"
-#include "../../lyon_b200/csrc/stroke_core.cuh"
+#include "../../lyon_b200/csrc/stroke_tile.cuh"
 
 using namespace lyc;
 
@@ -110,6 +110,128 @@ extern "C" int emul_stroke_batch(const lyon_path_batch* b, const lyon_stroke_opt
         sink.nv = sink.nt = 0;
         sink.base = (uint32_t)vertex_base + voff[s];
         stroke_slot(w, p, s, (uint32_t)vertex_base, sink, jcode.data(), nullptr);
+        if (sink.nv != nv || sink.nt != nt) status = LYON_ERR_INTERNAL;
+    }
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        uint32_t s_end = seg_off[b->path_verb_begin[path + 1]];
+        if (path_vertex_end) path_vertex_end[path] = voff[s_end];
+        if (path_index_end) path_index_end[path] = 3ull * toff[s_end];
+    }
+    *out_v = (lyon_stroke_vertex*)V;
+    *out_i = I;
+    *n_v = tv;
+    *n_i = 3ull * tt;
+    return status;
+}
+// The FUSED tile pipeline (tile_kernels.cuh) with the whole batch as one tile: the same per-item routines
+// (stroke_tile.cuh + stroke_core.cuh against TileViews), sequential loops in place of the block.
+extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t vertex_base,
+                                      lyon_stroke_vertex** out_v, uint64_t* n_v, uint32_t** out_i, uint64_t* n_i,
+                                      uint64_t* path_vertex_end, uint64_t* path_index_end) {
+    *out_v = nullptr;
+    *out_i = nullptr;
+    *n_v = *n_i = 0;
+    StrokeParams p = make_params(*o, b->num_attributes);
+    const uint32_t NV = b->n_verbs;
+    const V2* points = reinterpret_cast<const V2*>(b->points);
+    // phase 1a: plans + offsets
+    std::vector<VerbPlan> plans(NV);
+    std::vector<uint32_t> seg_pt(NV + 1), seg_off(NV + 1);
+    uint64_t pt = 0, so = 0;
+    for (uint32_t v = 0; v < NV; ++v) {
+        seg_pt[v] = (uint32_t)pt;
+        seg_off[v] = (uint32_t)so;
+        plans[v] = plan_verb(b->verbs[v], points, (uint32_t)pt, p.attr_stride, p.tolerance);
+        so += plans[v].nslots;
+        pt += verb_point_count(b->verbs[v], p.attr_stride);
+    }
+    seg_pt[NV] = (uint32_t)pt;
+    seg_off[NV] = (uint32_t)so;
+    if (so >= 0xFFFFFFF0ull) return LYON_ERR_TOO_MANY_VERTICES;
+    const uint32_t NS = (uint32_t)so;
+    std::vector<V2> pos(NS + 1);
+    std::vector<float> t(NS + 1), adv(NS + 1);
+    std::vector<uint32_t> src(NS + 1), voff(NS + 1), toff(NS + 1);
+    std::vector<uint8_t> flags(NS + 1, TF_END), jcode(NS + 1, 0);
+    TileViews w{};
+    w.pos = pos.data();
+    w.t = t.data();
+    w.adv = adv.data();
+    w.src = src.data();
+    w.flags = flags.data();
+    w.voff = voff.data();
+    w.toff = toff.data();
+    w.jcode = jcode.data();
+    w.n_slots = NS;
+    // phase 1b: slots of every verb
+    for (uint32_t v = 0; v < NV; ++v) {
+        uint8_t verb = b->verbs[v];
+        uint32_t ncurve = verb == VERB_QUAD ? 2u : (verb == VERB_CUBIC ? 3u : 1u);
+        tile_gen_verb(w, p, verb, points, seg_pt[v], plans[v], seg_off[v], seg_pt[v] + ncurve - 1u);
+    }
+    // phase 2: per path
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
+        tile_path_walk(w, p, seg_off[vb], seg_off[ve], vb < ve ? seg_pt[vb] : 0u);
+    }
+    // phase 3: classify + count
+    std::vector<uint32_t> cnt_v(NS + 1, 0), cnt_t(NS + 1, 0);
+    for (uint32_t s = 0; s < NS; ++s) {
+        SlotClass c = classify_slot(w, s);
+        uint32_t nv = 0, nt = 0;
+        uint8_t code = 0;
+        if (c.kind == KIND_JOIN) {
+            if (join_is_fast(w.P(c.pk), w.P(s), w.P(c.nk), (c.sf & SEG_FS_BIT) != 0u)) {
+                nv = 2u;
+                nt = (w.F(c.pk) & SEG_BEGIN_BIT) ? 0u : 2u;
+                code = JC_FAST | JC_SINGLE_POS | JC_SINGLE_NEG;
+            } else {
+                count_full_join(w, p, s, c.pk, c.nk, &nv, &nt, &code);
+            }
+        } else if (c.kind == KIND_END) {
+            CountSink sink;
+            sink.nv = sink.nt = 0;
+            sink.base = 0;
+            stroke_end_slot(w, p, s, 0u, sink);
+            nv = sink.nv;
+            nt = sink.nt;
+        }
+        cnt_v[s] = nv;
+        cnt_t[s] = nt;
+        jcode[s] = code;
+    }
+    uint64_t tv = 0, tt = 0;
+    for (uint32_t s = 0; s < NS; ++s) {  // voff aliases len: only overwritten after phase 2
+        voff[s] = (uint32_t)tv;
+        toff[s] = (uint32_t)tt;
+        tv += cnt_v[s];
+        tt += cnt_t[s];
+    }
+    voff[NS] = (uint32_t)tv;
+    toff[NS] = (uint32_t)tt;
+    if (tv > 0xFFFFFFFFull || tt > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (tv && vertex_base + tv - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    // phase 4: emit
+    GpuVertex* V = (GpuVertex*)malloc((tv ? tv : 1) * sizeof(GpuVertex));
+    uint32_t* I = (uint32_t*)malloc((tt ? tt : 1) * 12);
+    int status = LYON_OK;
+    for (uint32_t s = 0; s < NS; ++s) {
+        uint32_t nv = cnt_v[s], nt = cnt_t[s];
+        if ((nv | nt) == 0) continue;
+        EmitSink sink;
+        sink.vtx = V + voff[s];
+        sink.idx = I + 3ull * toff[s];
+        sink.nv = sink.nt = 0;
+        sink.base = (uint32_t)vertex_base + voff[s];
+        if (w.F(s) & SEG_END_BIT) {
+            stroke_end_slot(w, p, s, (uint32_t)vertex_base, sink);
+        } else {
+            uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
+            if (jcode[s] & JC_FAST)
+                emit_fast_join(w, p, s, pk, nk, (uint32_t)vertex_base, jcode.data(), sink);
+            else
+                emit_full_join(w, p, s, pk, nk, (uint32_t)vertex_base, jcode.data(), sink);
+        }
         if (sink.nv != nv || sink.nt != nt) status = LYON_ERR_INTERNAL;
     }
     for (uint32_t path = 0; path < b->n_paths; ++path) {

@@ -31,6 +31,8 @@ def lib():
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
                                         ctypes.c_void_p, ctypes.c_void_p]
+        L.emul_stroke_batch_tile.restype = ctypes.c_int
+        L.emul_stroke_batch_tile.argtypes = L.emul_stroke_batch.argtypes
         L.emul_free.argtypes = [ctypes.c_void_p]
         L.emul_flatten.restype = ctypes.c_uint64
         L.emul_flatten.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
@@ -45,8 +47,12 @@ class EmulError(Exception):
         self.code = code
 
 
-def stroke_batch(batch: PathBatch, opts: StrokeOptions, vertex_base: int = 0, with_ranges=False):
+PIPELINE = "general"  # or "tile": which device pipeline's per-item code stroke_batch emulates
+
+
+def stroke_batch(batch: PathBatch, opts: StrokeOptions, vertex_base: int = 0, with_ranges=False, pipeline=None):
     L = lib()
+    fn = L.emul_stroke_batch_tile if (pipeline or PIPELINE) == "tile" else L.emul_stroke_batch
     verbs = np.ascontiguousarray(batch.verbs, np.uint8)
     pts = np.ascontiguousarray(batch.points, np.float32)
     vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32)
@@ -58,7 +64,7 @@ def stroke_batch(batch: PathBatch, opts: StrokeOptions, vertex_base: int = 0, wi
     nv, ni = ctypes.c_uint64(), ctypes.c_uint64()
     pve = np.zeros(batch.n_paths, np.uint64)
     pie = np.zeros(batch.n_paths, np.uint64)
-    st = L.emul_stroke_batch(ctypes.byref(cb), ctypes.byref(co), vertex_base, ctypes.byref(pv), ctypes.byref(nv),
+    st = fn(ctypes.byref(cb), ctypes.byref(co), vertex_base, ctypes.byref(pv), ctypes.byref(nv),
                              ctypes.byref(pi), ctypes.byref(ni), pve.ctypes.data, pie.ctypes.data)
     if st != 0:
         if pv.value:

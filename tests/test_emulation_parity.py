@@ -13,6 +13,14 @@ from parity import assert_mesh_parity, bbox_extent
 GOLDEN = O.ROOT / "tests" / "golden"
 
 
+@pytest.fixture(autouse=True, params=["general", "tile"])
+def pipeline(request, monkeypatch):
+    """Every test runs against both device pipelines' per-item code: the general multi-kernel one
+    (stroke_core.cuh / Views) and the fused tile one (stroke_tile.cuh / TileViews)."""
+    monkeypatch.setattr(E, "PIPELINE", request.param)
+    return request.param
+
+
 def all_options(tol=0.1, width=1.0):
     for join in LineJoin:
         for cap in LineCap:
