@@ -140,6 +140,11 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, c
  * batch fits a tile), 1 = always the general multi-kernel pipeline (any path length).  Results are identical. */
 int lyon_cuda_set_pipeline(lyon_cuda_ctx* ctx, int pipeline);
 
+/* Device timing of the dominant kernel (the tile kernel of plan / emit / fused): when enabled the context brackets
+ * that launch with CUDA events on its stream; lyon_cuda_last_kernel_ms returns the duration of the last one. */
+int lyon_cuda_enable_timing(lyon_cuda_ctx* ctx, int on);
+int lyon_cuda_last_kernel_ms(lyon_cuda_ctx* ctx, float* ms);
+
 /* Synchronises and reads back the device-side consistency flag of the last emit: LYON_ERR_INTERNAL if the
  * emit pass ever produced a different number of vertices/triangles for a slot than the count pass planned. */
 int lyon_cuda_check(lyon_cuda_ctx* ctx);

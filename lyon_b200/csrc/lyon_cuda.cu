@@ -64,9 +64,11 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t 
         int64_t idx = look - (int64_t)lane;
         uint64_t d = ST_PREFIX;  // tiles before the first one: prefix 0
         if (idx >= 0) {
-            do {
+            d = ld_desc(&desc[idx]);
+            while ((d >> 62) == 0ull) {
+                __nanosleep(64);
                 d = ld_desc(&desc[idx]);
-            } while ((d >> 62) == 0ull);
+            }
         }
         unsigned pmask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
         uint64_t val = d & VAL_MASK;
@@ -534,12 +536,17 @@ struct lyon_cuda_ctx {
     size_t max_smem_optin = 0;
     Totals* h_totals = nullptr;  // pinned
     // fused tile pipeline
-    DevBuf path_slots, path_slot_begin, tile_first, tile_desc, tile_base, tile_misc;
+    DevBuf path_slots, path_events, path_slot_begin, path_event_begin, tile_first, tile_desc, tile_base, tile_misc;
     TileTotals* h_tile_totals = nullptr;  // pinned
     bool tile_planned = false;            // the last plan went through the tile pipeline
     lyon_path_batch tile_batch{};
     uint32_t tile_n_tiles = 0, tile_s_cap = 0, tile_w_v = 0, tile_w_t = 0, tile_quantum = 0;
+    int tile_nt = 256;
     int tile_force_general = 0;  // test hook: lyon_cuda_set_pipeline
+    // optional device timing of the dominant kernel (lyon_cuda_enable_timing)
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
     // state of the last plan
     bool planned = false;
     Views views{};
@@ -651,7 +658,7 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
 // ---------------------------------------------------------------------------------------------------------
 // Fused tile pipeline, host side
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TILE_NT = 256;
+
 // tile_misc layout: [0] TileTotals, [256..] tickets (4 x u32)
 TileTotals* d_tile_totals(lyon_cuda_ctx* c) { return reinterpret_cast<TileTotals*>(c->tile_misc.p); }
 uint32_t* d_tile_ticket(lyon_cuda_ctx* c, int i) { return reinterpret_cast<uint32_t*>(static_cast<char*>(c->tile_misc.p) + 256) + i; }
@@ -662,22 +669,39 @@ int fetch_tile_totals(lyon_cuda_ctx* c) {
     return LYON_OK;
 }
 
-// Tile geometry for a batch whose longest path feeds `max_path` slots.  Returns false when no configuration holds
-// such a path in shared memory (the general multi-kernel pipeline takes the batch instead).
-bool tile_config(const lyon_cuda_ctx* c, uint32_t max_path, uint32_t* s_cap, uint32_t* w_v, uint32_t* w_t, uint32_t* quantum) {
-    static const uint32_t caps[] = {1536u, 3072u, 6144u};
-    static const uint32_t wv[] = {768u, 768u, 384u};
-    for (int i = 0; i < 3; ++i) {
-        if (max_path > caps[i] / 2u) continue;
-        const uint32_t wt = wv[i] * 3u / 2u;
-        if (tile_smem_bytes(caps[i], wv[i], wt) > c->max_smem_optin) continue;
-        *s_cap = caps[i];
-        *w_v = wv[i];
-        *w_t = wt;
-        *quantum = caps[i] - (max_path ? max_path : 1u) + 1u;
-        return true;
+// Tile geometry for a batch whose longest path feeds `max_path` slots and that feeds `total` slots in all.
+// Default: 256 threads and 3520 slots per CTA, two CTAs per SM (each hides the other's serial phases; measured
+// best on C3, see profiles/).  Longer paths: one 512-thread CTA per SM with all its shared memory (~7000 slots).
+// The tile quantum shrinks for small batches so that every SM still gets a few tiles.  LYON_TILE=nt,cap,0 overrides.
+bool tile_config(const lyon_cuda_ctx* c, uint32_t max_path, unsigned long long total, TileGeom* g, uint32_t* quantum) {
+    TileGeom pick{};
+    bool found = false;
+    if (const char* e = getenv("LYON_TILE")) {
+        unsigned nt = 0, cap = 0, wv = 0;
+        if (sscanf(e, "%u,%u,%u", &nt, &cap, &wv) == 3 && (nt == 128 || nt == 256 || nt == 257 || nt == 512) && cap >= 64) {
+            pick = TileGeom{(int)nt, cap & ~31u, 0u, 0u};
+            found = max_path <= pick.s_cap;
+        }
     }
-    return false;
+    if (!found && max_path * 2u <= 3520u) {
+        pick = TileGeom{256, 3520u, 0u, 0u};
+        found = true;
+    }
+    if (!found) {
+        uint32_t cap = (uint32_t)((c->max_smem_optin - 2048) / 33u) & ~31u;
+        if (cap > 65000u) cap = 65000u & ~31u;
+        while (cap >= 256u && tile_smem_bytes(cap, 0, 0) > c->max_smem_optin) cap -= 32u;
+        if (cap < 256u || max_path > cap) return false;
+        pick = TileGeom{512, cap, 0u, 0u};
+    }
+    if (tile_smem_bytes(pick.s_cap, pick.w_v, pick.w_t) > c->max_smem_optin) return false;
+    *g = pick;
+    uint32_t q = pick.s_cap - (max_path ? max_path : 1u) + 1u;
+    const unsigned long long spread = total / (4ull * (unsigned long long)c->num_sms) + 1ull;  // >= 4 tiles per SM
+    if (spread < q) q = (uint32_t)(spread < 64ull ? 64ull : spread);
+    if (q > pick.s_cap - (max_path ? max_path : 1u) + 1u) q = pick.s_cap - (max_path ? max_path : 1u) + 1u;
+    *quantum = q;
+    return true;
 }
 
 // Pre-pass: per-path slot counts, their scan, the tile table.  *usable = the batch fits the tile pipeline.
@@ -686,19 +710,24 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     if (c->tile_force_general || !b->path_point_begin || b->n_paths == 0 || b->n_verbs == 0) return LYON_OK;
     const uint32_t np = b->n_paths;
     TRY(ensure(c, c->path_slots, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->path_events, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->path_slot_begin, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->path_event_begin, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->tile_misc, 512));
     const unsigned ptiles = grid_for(np, BLOCK * PSCAN_ITEMS);
-    TRY(ensure(c, c->tile_desc, (size_t)ptiles * 8));
+    TRY(ensure(c, c->tile_desc, (size_t)ptiles * 16));
     CU_TRY(c, cudaMemsetAsync(c->tile_misc.p, 0, 512, c->stream));
-    CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)ptiles * 8, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)ptiles * 16, c->stream));
     const unsigned warps_needed = np;
     unsigned blocks = (warps_needed + 7u) / 8u;
     if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
     k_path_slots<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
-                                               b->path_point_begin, np, c->params, (uint32_t*)c->path_slots.p, d_tile_totals(c));
-    k_scan_paths<<<ptiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->path_slots.p, np, (unsigned long long*)c->path_slot_begin.p,
-                                                 d_tile_ticket(c, 0), (uint64_t*)c->tile_desc.p, d_tile_totals(c));
+                                               b->path_point_begin, np, c->params, (uint32_t*)c->path_slots.p,
+                                               (uint32_t*)c->path_events.p, d_tile_totals(c));
+    k_scan_paths<<<ptiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->path_slots.p, (const uint32_t*)c->path_events.p, np,
+                                                 (unsigned long long*)c->path_slot_begin.p, (uint32_t*)c->path_event_begin.p,
+                                                 d_tile_ticket(c, 0), (uint64_t*)c->tile_desc.p,
+                                                 (uint64_t*)c->tile_desc.p + ptiles, d_tile_totals(c));
     c->launches += 2;
     CU_TRY(c, cudaGetLastError());
     TRY(fetch_tile_totals(c));
@@ -707,8 +736,11 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
         return LYON_ERR_INVALID_ARGUMENT;
     }
     const unsigned long long total = c->h_tile_totals->total_slots;
-    uint32_t s_cap, w_v, w_t, q;
-    if (!tile_config(c, c->h_tile_totals->max_path_slots, &s_cap, &w_v, &w_t, &q)) return LYON_OK;
+    TileGeom g;
+    uint32_t q;
+    if (!tile_config(c, c->h_tile_totals->max_path_slots, total, &g, &q)) return LYON_OK;
+    const uint32_t s_cap = g.s_cap, w_v = g.w_v, w_t = g.w_t;
+    c->tile_nt = g.nt;
     const unsigned long long n_tiles64 = total / q + 1ull;
     if (n_tiles64 > 0x7FFFFFFFull) return LYON_OK;
     c->tile_n_tiles = (uint32_t)n_tiles64;
@@ -728,6 +760,32 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     return LYON_OK;
 }
 
+template <int NT, int MODE, int MINB>
+int tile_launch_nt(lyon_cuda_ctx* c, const TileArgs& a) {
+    const size_t smem = tile_smem_bytes(a.s_cap, a.w_v, a.w_t);
+    auto kern = k_stroke_tile<NT, MODE, MINB>;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) {
+        c->err = "tile kernel does not fit on an SM";
+        return LYON_ERR_INTERNAL;
+    }
+    unsigned grid = (unsigned)c->num_sms * (unsigned)per_sm;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    CU_TRY(c, cudaMemsetAsync(a.ticket, 0, 4, c->stream));
+    if (MODE != TILE_MODE_EMIT) CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)c->tile_n_tiles * 16, c->stream));
+    if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    kern<<<grid, NT, smem, c->stream>>>(a, c->params);
+    if (c->timing) {
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
 template <int MODE>
 int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, uint64_t cap_v, uint64_t cap_t, uint64_t vertex_base,
                 uint64_t* d_path_vertex_end, uint64_t* d_path_index_end) {
@@ -738,6 +796,7 @@ int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, ui
     a.path_verb_begin = b.path_verb_begin;
     a.path_point_begin = b.path_point_begin;
     a.path_slot_begin = (const unsigned long long*)c->path_slot_begin.p;
+    a.path_event_begin = (const uint32_t*)c->path_event_begin.p;
     a.tile_first = (const uint32_t*)c->tile_first.p;
     a.n_tiles = c->tile_n_tiles;
     a.n_paths = b.n_paths;
@@ -757,23 +816,12 @@ int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, ui
     a.totals = d_tile_totals(c);
     a.path_vertex_end = (unsigned long long*)d_path_vertex_end;
     a.path_index_end = (unsigned long long*)d_path_index_end;
-    const size_t smem = tile_smem_bytes(a.s_cap, a.w_v, a.w_t);
-    auto kern = k_stroke_tile<TILE_NT, MODE>;
-    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE_NT, smem));
-    if (per_sm < 1) {
-        c->err = "tile kernel does not fit on an SM";
-        return LYON_ERR_INTERNAL;
+    switch (c->tile_nt) {
+        case 128: return tile_launch_nt<128, MODE, 4>(c, a);
+        case 512: return tile_launch_nt<512, MODE, 1>(c, a);
+        case 257: return tile_launch_nt<256, MODE, 3>(c, a);
+        default: return tile_launch_nt<256, MODE, 2>(c, a);
     }
-    unsigned grid = (unsigned)c->num_sms * (unsigned)per_sm;
-    if (grid > a.n_tiles) grid = a.n_tiles;
-    CU_TRY(c, cudaMemsetAsync(a.ticket, 0, 4, c->stream));
-    if (MODE != TILE_MODE_EMIT) CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)c->tile_n_tiles * 16, c->stream));
-    kern<<<grid, TILE_NT, smem, c->stream>>>(a, c->params);
-    c->launches++;
-    CU_TRY(c, cudaGetLastError());
-    return LYON_OK;
 }
 
 int tile_error(lyon_cuda_ctx* c) {
@@ -825,11 +873,13 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
-                      &c->path_slots, &c->path_slot_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
+                      &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_tile_totals) cudaFreeHost(c->h_tile_totals);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
 }
 
@@ -1038,6 +1088,25 @@ int lyon_cuda_check(lyon_cuda_ctx* c) {
         c->err = "internal: emit pass diverged from the count pass";
         return LYON_ERR_INTERNAL;
     }
+    return LYON_OK;
+}
+
+int lyon_cuda_enable_timing(lyon_cuda_ctx* c, int on) {
+    if (!c) return LYON_ERR_INVALID_ARGUMENT;
+    if (on && !c->ev0) {
+        CU_TRY(c, cudaEventCreate(&c->ev0));
+        CU_TRY(c, cudaEventCreate(&c->ev1));
+    }
+    c->timing = on != 0;
+    c->ev_valid = false;
+    return LYON_OK;
+}
+int lyon_cuda_last_kernel_ms(lyon_cuda_ctx* c, float* ms) {
+    if (!c || !ms) return LYON_ERR_INVALID_ARGUMENT;
+    *ms = 0.0f;
+    if (!c->ev_valid) return LYON_ERR_INVALID_ARGUMENT;
+    CU_TRY(c, cudaEventSynchronize(c->ev1));
+    CU_TRY(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
     return LYON_OK;
 }
 

@@ -77,7 +77,8 @@ struct Views {
 
 // The same slot arrays for ONE TILE of whole paths held in shared memory by the fused kernel (stroke_tile.cuh):
 // slot indices are tile-relative, flags are one byte (SEG_*_BIT >> 24), the endpoint id is stored per slot.
-static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08;
+static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08, TF_EVAL = 0x04, TF_CUBIC = 0x02,
+                     TF_LAST = 0x01;
 struct TileViews {
     V2* pos;
     float* t;

@@ -4,9 +4,10 @@
 // the last vertex written.  These are the per-verb / per-path routines it runs on that tile; like everything in
 // stroke_core.cuh they are LYC_HD so tests/emul can run the very same code on the CPU.
 //
-//   plan_verb        Wang counts of one verb (how many slots it feeds)                 [phase 1, thread per verb]
-//   tile_gen_verb    all slots of one verb, generated INCREMENTALLY (t1 = t0 + step)   [phase 1, thread per verb]
-//   tile_path_walk   merge filter + advancement chain + endpoint ids of one path       [phase 2, thread per path]
+//   plan_verb        Wang counts of one verb (how many slots it feeds)                 [phase 1a, thread per verb]
+//   tile_gen_verb    slots of one verb; for curves only the accumulated t of each      [phase 1a, thread per verb]
+//   tile_eval_slot   position + edge length of one curve slot from its t               [phase 1b, thread per slot]
+//   tile_path_walk   merge filter + advancement chain of one path                      [phase 2,  thread per path]
 #pragma once
 #include "stroke_core.cuh"
 
@@ -47,28 +48,27 @@ LYC_HD VerbPlan plan_verb(uint8_t verb, const V2* points, uint32_t pt, uint32_t 
 
 // One fed point: position, curve parameter, flags, endpoint id and |P - prev| with the "maybe mergeable" sign flag
 // (see point_gen_slot in stroke_core.cuh for the flag's meaning).
+LYC_HD float tile_len_flagged(const StrokeParams& p, V2 pos, V2 prev) {
+    V2 d = pos - prev;
+    float d2 = sqlen(d);
+    float l = sqrtf(d2);
+    if (!(d2 >= p.flag_thr)) l = -l;  // also flags NaN distances; -0.0f keeps the flag for zero length
+    return l;
+}
 LYC_HD void tile_put_slot(const TileViews& w, const StrokeParams& p, uint32_t s, V2 pos, V2 prev, bool has_prev, float t,
                           uint8_t fl, uint32_t src) {
     w.pos[s] = pos;
     w.t[s] = t;
     w.flags[s] = fl;
     w.src[s] = src;
-    float l = 0.0f;
-    if (has_prev) {
-        V2 d = pos - prev;
-        float d2 = sqlen(d);
-        l = sqrtf(d2);
-        if (!(d2 >= p.flag_thr)) l = -l;
-    }
-    w.len()[s] = l;
+    w.len()[s] = has_prev ? tile_len_flagged(p, pos, prev) : 0.0f;
 }
 
-// for_each_flattened_with_t of one quadratic (quadratic_bezier.rs:368-391) feeding slots s0.. .  With REMAP the
-// curve is one half of a quad split at `tsplit` by flatten_quad and t is mapped back onto the whole curve
-// (stroke.rs:2764 / 2770); is_flattening_step is decided on the un-mapped t of the half (stroke.rs:2765, 2771).
-template <bool REMAP>
-LYC_HD uint32_t tile_gen_quad(const TileViews& w, const StrokeParams& p, uint32_t s0, V2 from, V2 ctrl, V2 to, float n,
-                              bool remap_is_first_half, float tsplit, uint32_t src, uint8_t first_flag) {
+// for_each_flattened_with_t of one quadratic (quadratic_bezier.rs:368-391) feeding slots s0.. .  The curve is one
+// half of a quad split at `tsplit` by flatten_quad and t is mapped back onto the whole curve (stroke.rs:2764 /
+// 2770); is_flattening_step is decided on the un-mapped t of the half (stroke.rs:2765, 2771).
+LYC_HD uint32_t tile_gen_quad_half(const TileViews& w, const StrokeParams& p, uint32_t s0, V2 from, V2 ctrl, V2 to, float n,
+                                   bool first_half, float tsplit, uint32_t src, uint8_t first_flag) {
     const float step = 1.0f / n;
     const uint32_t cnt = to_u32_or_1(n);
     const QuadPoly poly = quad_poly(from, ctrl, to);
@@ -85,8 +85,7 @@ LYC_HD uint32_t tile_gen_quad(const TileViews& w, const StrokeParams& p, uint32_
             ts = 1.0f;
             pos = to;
         }
-        float t_out = ts;
-        if (REMAP) t_out = remap_is_first_half ? ts * tsplit : tsplit + ts * (1.0f - tsplit);
+        float t_out = first_half ? ts * tsplit : tsplit + ts * (1.0f - tsplit);
         uint8_t fl = (ts != 1.0f ? TF_FS : 0) | (k == 0u ? first_flag : 0);
         tile_put_slot(w, p, s0 + k, pos, prev, true, t_out, fl, src);
         prev = pos;
@@ -94,8 +93,11 @@ LYC_HD uint32_t tile_gen_quad(const TileViews& w, const StrokeParams& p, uint32_
     return cnt;
 }
 
-// Phase 1: every slot of verb `verb` (first stored point `pt`, first slot s0).  `src` is the tile-relative index of
-// the verb's endpoint in the point array (turned into an EndpointId by tile_path_walk).
+// Phase 1a (thread per verb): every slot of verb `verb` (first stored point `pt`, first slot s0, EndpointId `src`).
+// Single-slot verbs and the rare split quadratics are finished here.  For ordinary curves only the SEQUENTIAL part
+// runs here -- the accumulated parameter t1 = t0 + step of for_each_flattened_with_t (cubic_bezier.rs:605-611,
+// quadratic_bezier.rs:382-388) -- and each slot is left marked TF_EVAL with the verb's point index parked in `adv`;
+// phase 1b evaluates the positions with one thread per slot (no divergence between curves of different counts).
 LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t verb, const V2* points, uint32_t pt,
                           const VerbPlan& plan, uint32_t s0, uint32_t src) {
     const uint32_t a = p.attr_stride;
@@ -106,41 +108,32 @@ LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t ver
         case VERB_LINE:
             tile_put_slot(w, p, s0, points[pt], seg_from_point(points, pt, a), true, 1.0f, TF_FIRST, src);
             break;
-        case VERB_CUBIC: {  // cubic_bezier.rs:590-614
-            const V2 from = seg_from_point(points, pt, a);
-            const V2 to = points[pt + 2];
+        case VERB_CUBIC:
+        case VERB_QUAD: {
+            if (verb == VERB_QUAD && plan.tsplit >= 0.0f) {
+                const V2 from = seg_from_point(points, pt, a);
+                const V2 ctrl = points[pt], to = points[pt + 1];
+                const float ts = plan.tsplit;
+                const V2 sp = quad_sample(from, ctrl, to, ts);
+                uint32_t n1 = tile_gen_quad_half(w, p, s0, from, lerp(from, ctrl, ts), sp, plan.n_a, true, ts, src, TF_FIRST);
+                tile_gen_quad_half(w, p, s0 + n1, sp, lerp(ctrl, to, ts), to, plan.n_b, false, ts, src, 0);
+                break;
+            }
             const float step = 1.0f / plan.n_a;
             const uint32_t cnt = to_u32_or_1(plan.n_a);
-            const CubicPoly poly = cubic_poly(from, points[pt], points[pt + 1], to);
+            const uint8_t kind = TF_EVAL | (verb == VERB_CUBIC ? TF_CUBIC : 0);
+            const float ptbits = u2f(pt);
             float t = 0.0f;
-            V2 prev = from;
             for (uint32_t k = 0; k < cnt; ++k) {
-                V2 pos;
-                float ts;
+                float ts = 1.0f;
                 if (k + 1u < cnt) {
                     t = t + step;
                     ts = t;
-                    pos = cubic_poly_sample(poly, t);
-                } else {
-                    ts = 1.0f;
-                    pos = to;
                 }
-                uint8_t fl = (ts != 1.0f ? TF_FS : 0) | (k == 0u ? TF_FIRST : 0);
-                tile_put_slot(w, p, s0 + k, pos, prev, true, ts, fl, src);
-                prev = pos;
-            }
-            break;
-        }
-        case VERB_QUAD: {
-            const V2 from = seg_from_point(points, pt, a);
-            const V2 ctrl = points[pt], to = points[pt + 1];
-            if (plan.tsplit >= 0.0f) {
-                const float ts = plan.tsplit;
-                const V2 sp = quad_sample(from, ctrl, to, ts);
-                uint32_t n1 = tile_gen_quad<true>(w, p, s0, from, lerp(from, ctrl, ts), sp, plan.n_a, true, ts, src, TF_FIRST);
-                tile_gen_quad<true>(w, p, s0 + n1, sp, lerp(ctrl, to, ts), to, plan.n_b, false, ts, src, 0);
-            } else {
-                tile_gen_quad<false>(w, p, s0, from, ctrl, to, plan.n_a, false, 0.0f, src, TF_FIRST);
+                w.t[s0 + k] = ts;
+                w.flags[s0 + k] = kind | (ts != 1.0f ? TF_FS : 0) | (k == 0u ? TF_FIRST : 0) | (k + 1u < cnt ? 0 : TF_LAST);
+                w.src[s0 + k] = src;
+                w.adv[s0 + k] = ptbits;
             }
             break;
         }
@@ -153,19 +146,80 @@ LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t ver
     }
 }
 
+// Phase 1b (thread per slot): position of a TF_EVAL slot from its t (polynomial form, cubic_bezier.rs:1318-1365 /
+// quadratic_bezier.rs:891-939; the last point of a curve is the exact endpoint) and its distance to the previous fed
+// point (the previous sample of the same curve is re-evaluated rather than read, so the phase needs no ordering).
+LYC_HD void tile_eval_slot(const TileViews& w, const StrokeParams& p, const V2* points, uint32_t s) {
+    const uint8_t fl = w.flags[s];
+    if (!(fl & TF_EVAL)) return;
+    const uint32_t pt = f2u(w.adv[s]);
+    const float t = w.t[s];
+    const V2 from = seg_from_point(points, pt, p.attr_stride);
+    V2 pos, prev;
+    if (fl & TF_CUBIC) {
+        const V2 to = points[pt + 2];
+        const CubicPoly poly = cubic_poly(from, points[pt], points[pt + 1], to);
+        pos = (fl & TF_LAST) ? to : cubic_poly_sample(poly, t);
+        prev = (fl & TF_FIRST) ? from : cubic_poly_sample(poly, w.t[s - 1u]);
+    } else {
+        const V2 to = points[pt + 1];
+        const QuadPoly poly = quad_poly(from, points[pt], to);
+        pos = (fl & TF_LAST) ? to : quad_poly_sample(poly, t);
+        prev = (fl & TF_FIRST) ? from : quad_poly_sample(poly, w.t[s - 1u]);
+    }
+    w.pos[s] = pos;
+    w.len()[s] = tile_len_flagged(p, pos, prev);
+}
+// Phase 1c: a slot is "special" for the walk when it is not an ordinary kept point: Begin, End, or possibly within
+// the merge distance of its predecessor.
+LYC_HD bool tile_slot_special(const TileViews& w, uint32_t s) {
+    return (w.flags[s] & (TF_BEGIN | TF_END)) != 0 || len_flagged(w.len()[s]);
+}
+
 // Phase 2: one path = slots [sa, sb) of the tile, sequential.  Same chains as path_walk (stroke_core.cuh):
 // merge filter against the last kept point (stroke.rs:1318-1320, 1530-1536), advancement (stroke.rs:1546-1550,
 // 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), may_need_empty_cap (stroke.rs:1180,
-// 1533) and endpoint ids: sequential per event (stroke.rs:882-937) or point-array offsets (path.rs:1197-1263).
-// `pt_rel` = index of the path's first stored point relative to the tile's first point.
-LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t sa, uint32_t sb, uint32_t pt_rel) {
+// 1533).  `special` holds one bit per slot (phase 1c): aligned groups of 32 ordinary points -- the overwhelmingly
+// common case -- reduce to the bare f32 addition chain on vector loads/stores.
+LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t sa, uint32_t sb, const uint32_t* special) {
     const float nan = u2f(0x7FC00000u);
     float carry = 0.0f, adv = 0.0f;
-    uint32_t evt = 0, begin_slot = sa, last_kept = sa, m = 0, cur_id = 0;
+    uint32_t begin_slot = sa, last_kept = sa, m = 0;
     bool mnec = false;
-    const bool with_ids = p.num_attributes > 0;
     float* len = w.len();
-    for (uint32_t s = sa; s < sb; ++s) {
+    uint32_t s = sa;
+    while (s < sb) {
+        if ((s & 3u) == 0u && s + 32u <= sb && m >= 1u && last_kept == s - 1u) {
+            // special bits of slots [s, s + 32)
+            const uint32_t sh = s & 31u;
+            uint32_t bits = special[s >> 5] >> sh;
+            if (sh) bits |= special[(s >> 5) + 1u] << (32u - sh);
+            if (bits == 0u) {
+#ifdef __CUDA_ARCH__
+                const float4* l4 = reinterpret_cast<const float4*>(len + s);
+                float4* a4 = reinterpret_cast<float4*>(w.adv + s);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 l = l4[q];
+                    float4 a;
+                    a.x = adv = adv + l.x;
+                    a.y = adv = adv + l.y;
+                    a.z = adv = adv + l.z;
+                    a.w = adv = adv + l.w;
+                    a4[q] = a;
+                }
+#else
+                for (uint32_t q = 0; q < 32u; ++q) {
+                    adv = adv + len[s + q];
+                    w.adv[s + q] = adv;
+                }
+#endif
+                m += 32u;
+                last_kept = s + 31u;
+                s += 32u;
+                continue;
+            }
+        }
         const uint8_t fl = w.flags[s];
         if (fl & TF_BEGIN) {
             begin_slot = s;
@@ -174,8 +228,6 @@ LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t s
             mnec = false;
             adv = carry;
             w.adv[s] = adv;
-            w.src[s] = with_ids ? (w.src[s] - pt_rel) : evt;
-            evt++;
         } else if (fl & TF_END) {
             const bool close = (fl & TF_CLOSE) != 0;
             if (close && m == 1u) mnec = true;
@@ -187,26 +239,26 @@ LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t s
             if (!(close && m > 2u) && m >= 2u) carry = adv;
             m = 0;
         } else {
-            if (fl & TF_FIRST) {
-                cur_id = with_ids ? (w.src[s] - pt_rel) : evt;
-                evt++;
-            }
-            w.src[s] = cur_id;
             float l = len[s];
+            bool keep = true;
             if (len_flagged(l) || last_kept != s - 1u) {
                 V2 pl = w.pos[last_kept], ps = w.pos[s];
                 if (sqlen(pl - ps) < p.merge_thr) {
                     w.adv[s] = nan;
                     if (m == 1u) mnec = true;
-                    continue;
+                    keep = false;
+                } else {
+                    l = length(ps - pl);
                 }
-                l = length(ps - pl);
             }
-            adv = adv + l;
-            w.adv[s] = adv;
-            last_kept = s;
-            m++;
+            if (keep) {
+                adv = adv + l;
+                w.adv[s] = adv;
+                last_kept = s;
+                m++;
+            }
         }
+        ++s;
     }
 }
 

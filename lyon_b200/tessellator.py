@@ -173,6 +173,17 @@ class DeviceTessellator:
         if st != 0:
             _raise(self.L, self.ctx, st)
 
+    def enable_timing(self, on: bool = True):
+        self.L.lyon_cuda_enable_timing(self.ctx, 1 if on else 0)
+
+    def last_kernel_ms(self) -> float:
+        """CUDA-event duration of the last tile kernel launch (needs enable_timing)."""
+        ms = ctypes.c_float()
+        st = self.L.lyon_cuda_last_kernel_ms(self.ctx, ctypes.byref(ms))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return float(ms.value)
+
     def check(self):
         st = self.L.lyon_cuda_check(self.ctx)
         if st != 0:
@@ -318,8 +329,6 @@ class HostPipeline:
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
             self.tz = [DeviceTessellator(self.device.index, stream=s) for s in self.streams]
-        self.dev_v = [None, None]
-        self.dev_i = [None, None]
         self.out_v = None
         self.out_i = None
         self.h2d_bytes = 0
@@ -335,20 +344,10 @@ class HostPipeline:
         self.pb = np.ascontiguousarray(batch.path_point_begin, np.uint32).astype(np.int64)
         n = batch.n_paths
         self.cuts = list(range(0, n, self.chunk_paths)) + [n]
-        self.p_ranges = []
+        self.p_ranges, self.p_pranges = [], []
         for lo, hi in zip(self.cuts[:-1], self.cuts[1:]):
-            r = torch.from_numpy((self.vb[lo:hi + 1] - self.vb[lo]).astype(np.int32)).pin_memory()
-            self.p_ranges.append(r)
-
-    def _ensure(self, which, k, rows, cols, dtype):
-        torch = self.torch
-        cur = (self.dev_v if which == "v" else self.dev_i)[k]
-        if cur is None or cur.shape[0] < rows:
-            shape = (int(rows * 1.1) + 16, cols) if cols else (int(rows * 1.1) + 16,)
-            t = torch.empty(shape, dtype=dtype, device=self.device)
-            (self.dev_v if which == "v" else self.dev_i)[k] = t
-            return t
-        return cur
+            self.p_ranges.append(torch.from_numpy((self.vb[lo:hi + 1] - self.vb[lo]).astype(np.int32)).pin_memory())
+            self.p_pranges.append(torch.from_numpy((self.pb[lo:hi + 1] - self.pb[lo]).astype(np.int32)).pin_memory())
 
     def run(self, options: StrokeOptions):
         """One end-to-end pass. Returns (n_vertices, n_indices); results are in self.out_v[:nv], self.out_i[:ni]."""
@@ -367,16 +366,15 @@ class HostPipeline:
                     d.verbs = self.p_verbs[v0:v1].to(self.device, non_blocking=True)
                     d.points = self.p_points[2 * p0:2 * p1].to(self.device, non_blocking=True)
                     d.path_verb_begin = self.p_ranges[c].to(self.device, non_blocking=True)
-                    d.path_point_begin = d.path_verb_begin
-                    self.h2d_bytes += (v1 - v0) + 8 * (p1 - p0) + 4 * (hi - lo + 1)
-                    nv, ni = tz.stroke_plan(d, options)  # syncs stream k only
+                    d.path_point_begin = self.p_pranges[c].to(self.device, non_blocking=True)
+                    self.h2d_bytes += (v1 - v0) + 8 * (p1 - p0) + 8 * (hi - lo + 1)
+                    # single pass into this context's own grow-only device buffers (syncs stream k only)
+                    dv, di = tz.stroke_fused(d, options, vertex_base=tot_v)
+                    nv, ni = int(dv.shape[0]), int(di.shape[0])
                     if tot_v + nv > 0xFFFFFFFF:
                         raise TooManyVertices(_ffi.ERR_TOO_MANY_VERTICES, "TooManyVertices")
-                    dv = self._ensure("v", k, nv, 8, torch.float32)
-                    di = self._ensure("i", k, ni, 0, torch.int32)
                     if self.out_v is None or self.out_v.shape[0] < tot_v + nv or self.out_i.shape[0] < tot_i + ni:
                         self._grow_outputs(tot_v + nv, tot_i + ni, c + 1, tot_v, tot_i)
-                    tz.stroke_emit(nv, ni, vertex_base=tot_v, vertices=dv, indices=di)
                     self.out_v[tot_v:tot_v + nv].copy_(dv[:nv], non_blocking=True)
                     self.out_i[tot_i:tot_i + ni].copy_(di[:ni], non_blocking=True)
                     self.d2h_bytes += 32 * nv + 4 * ni

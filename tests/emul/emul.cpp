@@ -163,16 +163,28 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     w.toff = toff.data();
     w.jcode = jcode.data();
     w.n_slots = NS;
-    // phase 1b: slots of every verb
+    // phase 1a: slots of every verb (curves: accumulated t only); EndpointIds per path
+    std::vector<uint32_t> verb_path(NV, 0), evt_before(NV + 1, 0);
+    for (uint32_t path = 0; path < b->n_paths; ++path)
+        for (uint32_t v = b->path_verb_begin[path]; v < b->path_verb_begin[path + 1]; ++v) verb_path[v] = path;
+    for (uint32_t v = 0; v < NV; ++v)
+        evt_before[v + 1] = evt_before[v] + ((b->verbs[v] != VERB_END && b->verbs[v] != VERB_CLOSE) ? 1u : 0u);
     for (uint32_t v = 0; v < NV; ++v) {
         uint8_t verb = b->verbs[v];
         uint32_t ncurve = verb == VERB_QUAD ? 2u : (verb == VERB_CUBIC ? 3u : 1u);
-        tile_gen_verb(w, p, verb, points, seg_pt[v], plans[v], seg_off[v], seg_pt[v] + ncurve - 1u);
+        uint32_t vb = b->path_verb_begin[verb_path[v]];
+        uint32_t id = p.num_attributes > 0 ? (seg_pt[v] - seg_pt[vb]) + ncurve - 1u : evt_before[v] - evt_before[vb];
+        tile_gen_verb(w, p, verb, points, seg_pt[v], plans[v], seg_off[v], id);
     }
+    // phase 1b: curve positions per slot; 1c: special mask
+    for (uint32_t s = 0; s < NS; ++s) tile_eval_slot(w, p, points, s);
+    std::vector<uint32_t> special(NS / 32 + 2, 0);
+    for (uint32_t s = 0; s < NS; ++s)
+        if (tile_slot_special(w, s)) special[s >> 5] |= 1u << (s & 31u);
     // phase 2: per path
     for (uint32_t path = 0; path < b->n_paths; ++path) {
         uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
-        tile_path_walk(w, p, seg_off[vb], seg_off[ve], vb < ve ? seg_pt[vb] : 0u);
+        tile_path_walk(w, p, seg_off[vb], seg_off[ve], special.data());
     }
     // phase 3: classify + count
     std::vector<uint32_t> cnt_v(NS + 1, 0), cnt_t(NS + 1, 0);
