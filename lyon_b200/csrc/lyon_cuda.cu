@@ -669,6 +669,10 @@ int fetch_tile_totals(lyon_cuda_ctx* c) {
     return LYON_OK;
 }
 
+struct TileGeom {
+    int nt;                   // threads per CTA (128 / 256 / 512)
+    uint32_t s_cap, w_v, w_t;  // slot capacity (w_v / w_t: unused staging sizes, kept 0)
+};
 // Tile geometry for a batch whose longest path feeds `max_path` slots and that feeds `total` slots in all.
 // Default: 256 threads and 3520 slots per CTA, two CTAs per SM (each hides the other's serial phases; measured
 // best on C3, see profiles/).  Longer paths: one 512-thread CTA per SM with all its shared memory (~7000 slots).
