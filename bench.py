@@ -180,6 +180,7 @@ def main():
     import torch.distributed as dist
     import workloads as W
     from lyon_b200 import DeviceTessellator, HostPipeline
+    from lyon_b200.sharding import exchange_totals
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,8 +221,6 @@ def main():
     torch.cuda.synchronize()
 
     verts = idx = None
-    totals = torch.zeros(2, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
     tz.enable_timing(True)
     kernel_ms = []
 
@@ -236,10 +235,7 @@ def main():
             nv, ni = int(v.shape[0]), int(i.shape[0])
         else:
             nv, ni = tz.stroke_plan(dbatch, opts)
-            totals[0], totals[1] = nv, ni
-            dist.all_gather_into_tensor(gathered, totals)
-            g = gathered.cpu().numpy().reshape(world, 2)
-            base = int(g[:rank, 0].sum())
+            base, _ibase, _tot = exchange_totals(nv, ni, device=dev)  # the one collective: 16 B per rank over NCCL
             if verts is None or verts.shape[0] < nv or idx.shape[0] < ni:
                 verts = torch.empty((nv, 8), dtype=torch.float32, device=dev)
                 idx = torch.empty((ni,), dtype=torch.int32, device=dev)

@@ -7,6 +7,7 @@ point raises if the CUDA library or a device is missing.
 from .geometry import STROKE_VERTEX_DTYPE, TessellationError, TooManyVertices, VertexBuffers
 from .options import LineCap, LineJoin, StrokeOptions
 from .path import Path, PathBatch, PathBuilder, SvgPathBuilder, parse_svg_path
+from .sharding import ShardedStroker, exchange_totals, partition_by_cost
 from .tessellator import (DeviceBatch, DeviceTessellator, HostPipeline, StrokeTessellator, device_mesh_to_host, flatten_cubics,
                           flatten_quadratics, tessellate_paths)
 
@@ -15,5 +16,5 @@ __all__ = [
     "LineCap", "LineJoin", "StrokeOptions",
     "VertexBuffers", "STROKE_VERTEX_DTYPE", "TessellationError", "TooManyVertices",
     "DeviceBatch", "DeviceTessellator", "HostPipeline", "StrokeTessellator", "tessellate_paths", "device_mesh_to_host",
-    "flatten_cubics", "flatten_quadratics",
+    "flatten_cubics", "flatten_quadratics", "ShardedStroker", "exchange_totals", "partition_by_cost",
 ]

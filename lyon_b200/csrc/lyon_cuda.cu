@@ -479,36 +479,105 @@ __global__ void __launch_bounds__(BLOCK) k_flat_count(const float* __restrict__ 
         totals->flat_points = s_base + local + cnt;
     }
 }
+// Emit pass of the standalone curve flattener.  A block owns FLAT_CURVES consecutive curves and walks their output
+// points in windows of FLAT_WINDOW:
+//   phase A  thread / curve   the SEQUENTIAL part only: t1 = t0 + step replayed in f32 (cubic_bezier.rs:605-611,
+//                             quadratic_bezier.rs:382-388); each t and its curve id go to shared memory.  The
+//                             polynomial coefficients (cubic_bezier.rs:1318-1325) are computed once per curve.
+//   phase B  thread / point   Horner evaluation (cubic_bezier.rs:1351-1365), the last point of a curve is the exact
+//                             endpoint; a warp stores 32 consecutive points = 256 contiguous bytes.
+// HBM traffic: control points and offsets once, every output point once.
+constexpr int FLAT_CURVES = 256;
+constexpr int FLAT_WINDOW = 8192;
+constexpr uint16_t FLAT_LAST = 0x8000u;
 template <int NPTS>
-__global__ void __launch_bounds__(BLOCK) k_flat_emit(const float* __restrict__ ctrl, unsigned long long n, float tol,
-                                                     const unsigned long long* __restrict__ offsets,
-                                                     float2* __restrict__ out, float* __restrict__ t_out) {
-    __shared__ unsigned long long s_off[BLOCK + 1];
-    __shared__ float s_ctrl[BLOCK * 2 * NPTS];
-    const unsigned long long c0 = (unsigned long long)blockIdx.x * BLOCK;
-    const uint32_t nc = (uint32_t)min((unsigned long long)BLOCK, n - c0);
-    for (uint32_t i = threadIdx.x; i <= nc; i += BLOCK) s_off[i] = offsets[c0 + i];
-    for (uint32_t i = threadIdx.x; i < nc * 2u * NPTS; i += BLOCK) s_ctrl[i] = ctrl[c0 * 2ull * NPTS + i];
+struct FlatSmem {
+    unsigned long long off[FLAT_CURVES + 1];
+    float poly[FLAT_CURVES][2 * NPTS];  // a0..a(NPTS-1), then nothing: `to` lives in `to[]`
+    float to[FLAT_CURVES][2];
+    float t[FLAT_WINDOW];
+    uint16_t cid[FLAT_WINDOW];
+};
+template <int NPTS>
+__global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restrict__ ctrl, unsigned long long n, float tol,
+                                                           const unsigned long long* __restrict__ offsets,
+                                                           float2* __restrict__ out, float* __restrict__ t_out) {
+    extern __shared__ __align__(16) unsigned char flat_smem_raw[];
+    FlatSmem<NPTS>& sm = *reinterpret_cast<FlatSmem<NPTS>*>(flat_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * FLAT_CURVES;
+    const uint32_t nc = (uint32_t)min((unsigned long long)FLAT_CURVES, n - c0);
+    for (uint32_t i = tid; i <= nc; i += FLAT_CURVES) sm.off[i] = offsets[c0 + i];
+    // stage the control points through the (not yet used) t window: coalesced 4-byte loads
+    float* stage = sm.t;
+    for (uint32_t i = tid; i < nc * 2u * NPTS; i += FLAT_CURVES) stage[i] = ctrl[c0 * 2ull * NPTS + i];
     __syncthreads();
-    const unsigned long long base = s_off[0];
-    const unsigned long long total = s_off[nc] - base;
-    for (unsigned long long i = threadIdx.x; i < total; i += BLOCK) {
-        const unsigned long long s = base + i;
-        uint32_t lo = 0, hi = nc;
-        while (hi - lo > 1u) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (s_off[mid] <= s) lo = mid; else hi = mid;
+    float step = 0.0f, t = 0.0f;
+    uint32_t cnt = 0u, k = 0u;
+    if (tid < nc) {
+        const float* c = stage + tid * 2u * NPTS;
+        float nseg;
+        if (NPTS == 4) {
+            const V2 from = v2(c[0], c[1]), c1 = v2(c[2], c[3]), c2 = v2(c[4], c[5]), to = v2(c[6], c[7]);
+            nseg = cubic_wang(from, c1, c2, to, tol);
+            const CubicPoly q = cubic_poly(from, c1, c2, to);
+            float* d = sm.poly[tid];
+            d[0] = q.a0.x; d[1] = q.a0.y; d[2] = q.a1.x; d[3] = q.a1.y;
+            d[4] = q.a2.x; d[5] = q.a2.y; d[6] = q.a3.x; d[7] = q.a3.y;
+            sm.to[tid][0] = to.x;
+            sm.to[tid][1] = to.y;
+        } else {
+            const V2 from = v2(c[0], c[1]), cc = v2(c[2], c[3]), to = v2(c[4], c[5]);
+            nseg = quad_wang(from, cc, to, tol);
+            const QuadPoly q = quad_poly(from, cc, to);
+            float* d = sm.poly[tid];
+            d[0] = q.a0.x; d[1] = q.a0.y; d[2] = q.a1.x; d[3] = q.a1.y; d[4] = q.a2.x; d[5] = q.a2.y;
+            sm.to[tid][0] = to.x;
+            sm.to[tid][1] = to.y;
         }
-        const float* c = s_ctrl + lo * 2u * NPTS;
-        const uint32_t k = (uint32_t)(s - s_off[lo]);
-        V2 pos, prev;
-        float t;
-        if (NPTS == 4)
-            cubic_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), tol, k, &pos, &prev, &t);
-        else
-            quad_point(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), tol, k, &pos, &prev, &t);
-        out[s] = make_float2(pos.x, pos.y);
-        if (t_out) t_out[s] = t;
+        step = 1.0f / nseg;
+        cnt = to_u32_or_1(nseg);
+    }
+    __syncthreads();  // `stage` (= sm.t) is free again
+    const unsigned long long base = sm.off[0];
+    const unsigned long long total = sm.off[nc] - base;
+    const unsigned long long my0 = tid < nc ? sm.off[tid] - base : 0ull;  // block-relative index of my first point
+    for (unsigned long long w0 = 0; w0 < total; w0 += FLAT_WINDOW) {
+        const unsigned long long w1 = min(total, w0 + (unsigned long long)FLAT_WINDOW);
+        // ---- phase A
+        while (k < cnt && my0 + k < w1) {
+            const bool last = k + 1u == cnt;
+            if (!last) t = t + step;
+            const uint32_t i = (uint32_t)(my0 + k - w0);
+            sm.t[i] = last ? 1.0f : t;
+            sm.cid[i] = (uint16_t)(tid | (last ? FLAT_LAST : 0u));
+            ++k;
+        }
+        __syncthreads();
+        // ---- phase B
+        const uint32_t wn = (uint32_t)(w1 - w0);
+        for (uint32_t i = tid; i < wn; i += FLAT_CURVES) {
+            const uint16_t cw = sm.cid[i];
+            const uint32_t c = cw & 0xFFu;
+            const float tt = sm.t[i];
+            const float* d = sm.poly[c];
+            V2 pos;
+            if (cw & FLAT_LAST) {
+                pos = v2(sm.to[c][0], sm.to[c][1]);
+            } else if (NPTS == 4) {
+                CubicPoly q;
+                q.a0 = v2(d[0], d[1]); q.a1 = v2(d[2], d[3]); q.a2 = v2(d[4], d[5]); q.a3 = v2(d[6], d[7]);
+                pos = cubic_poly_sample(q, tt);
+            } else {
+                QuadPoly q;
+                q.a0 = v2(d[0], d[1]); q.a1 = v2(d[2], d[3]); q.a2 = v2(d[4], d[5]);
+                pos = quad_poly_sample(q, tt);
+            }
+            const unsigned long long s = base + w0 + i;
+            __stcs(out + s, make_float2(pos.x, pos.y));
+            if (t_out) __stcs(t_out + s, tt);
+        }
+        __syncthreads();
     }
 }
 
@@ -647,8 +716,10 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
                  float* d_points, float* d_t) {
     if (!c || (n && (!d_ctrl || !d_offsets)) || (total && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
     if (n == 0 || total == 0) return LYON_OK;
-    k_flat_emit<NPTS><<<grid_for(n, BLOCK), BLOCK, 0, c->stream>>>(d_ctrl, n, tol, (const unsigned long long*)d_offsets,
-                                                                  (float2*)d_points, d_t);
+    const size_t smem = sizeof(FlatSmem<NPTS>);
+    CU_TRY(c, cudaFuncSetAttribute(k_flat_emit<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_flat_emit<NPTS><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, (const unsigned long long*)d_offsets,
+                                                                                 (float2*)d_points, d_t);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return LYON_OK;

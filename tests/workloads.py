@@ -177,10 +177,4 @@ def c3_batch_range(lo: int, hi: int, n_segments: int = 64, seed: int = 2024) -> 
     return concat_batches(out)
 
 
-def partition_by_cost(path_verb_begin: np.ndarray, n_ranks: int) -> np.ndarray:
-    """Cut a batch into n_ranks contiguous path ranges of ~equal cumulative segment (verb) count.
-    Returns n_ranks + 1 path indices."""
-    total = int(path_verb_begin[-1])
-    targets = (np.arange(1, n_ranks) * total) // n_ranks
-    cuts = np.searchsorted(path_verb_begin, targets, side="left")
-    return np.concatenate([[0], cuts, [len(path_verb_begin) - 1]]).astype(np.int64)
+from lyon_b200.sharding import partition_by_cost  # noqa: E402,F401  (the product owns the partitioner)
