@@ -4,11 +4,13 @@ The product path fails loudly when the CUDA library is missing: there is no CPU 
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 from .options import CStrokeOptions
 
-_LIB_PATH = Path(__file__).resolve().parent / "liblyon_cuda.so"
+# LYON_CUDA_LIB points at an alternative build of the same library (instrumented builds of tools/dev_build.sh)
+_LIB_PATH = Path(os.environ.get("LYON_CUDA_LIB") or Path(__file__).resolve().parent / "liblyon_cuda.so")
 _LIB = None
 
 LYON_OK = 0

@@ -9,9 +9,13 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define LYC_HD __host__ __device__ __forceinline__
+// Real function calls for the heavy, rarely taken routines (caps, closing joins, arcs): the tile kernel's code must
+// stay small enough for the instruction cache.
+#define LYC_NOINLINE static __host__ __device__ __noinline__
 #else
 // Host-only build (tests/emul): the same source compiled by g++ -ffp-contract=off emulates the kernels.
 #define LYC_HD inline
+#define LYC_NOINLINE static inline
 #endif
 
 #if defined(__FAST_MATH__) || defined(__USE_FAST_MATH__)
@@ -60,11 +64,12 @@ LYC_HD float fast_atan2(float y, float x) {
 LYC_HD float angle_from_x_axis(V2 v) { return fast_atan2(v.y, v.x); }
 // fmodf(x, m) for m > 0, exact like the libm routine.  |x| < m returns x; m <= |x| < 2m returns x -/+ m, which is
 // exact (Sterbenz: m <= |x| <= 2m); everything else (incl. NaN/inf) goes to fmodf.
+LYC_NOINLINE float fmod_rare(float x, float m) { return fmodf(x, m); }
 LYC_HD float fmod_small(float x, float m) {
     float ax = fabsf(x);
     if (ax < m) return x;
     if (ax < 2.0f * m) return x < 0.0f ? x + m : x - m;
-    return fmodf(x, m);
+    return fmod_rare(x, m);
 }
 // euclid Angle::angle_to
 LYC_HD float angle_to(float self, float to) {
@@ -74,16 +79,15 @@ LYC_HD float angle_to(float self, float to) {
 }
 // Rust f32::{cos,sin,acos,asin,log2} call the platform libm; both sides evaluate in double and round
 // once (DESIGN.md "Transcendentals").
-LYC_HD float libm_cos(float a) { return (float)cos((double)a); }
-LYC_HD float libm_sin(float a) { return (float)sin((double)a); }
-LYC_HD float libm_acos(float a) { return (float)acos((double)a); }
-LYC_HD float libm_asin(float a) { return (float)asin((double)a); }
-LYC_HD float libm_log2(float a) { return (float)log2((double)a); }
-LYC_HD void libm_sincos(float a, float* sn, float* cs) {
+LYC_NOINLINE float libm_cos(float a) { return (float)cos((double)a); }
+LYC_NOINLINE float libm_sin(float a) { return (float)sin((double)a); }
+LYC_NOINLINE float libm_acos(float a) { return (float)acos((double)a); }
+LYC_NOINLINE float libm_asin(float a) { return (float)asin((double)a); }
+LYC_NOINLINE float libm_log2(float a) { return (float)log2((double)a); }
+LYC_NOINLINE V2 libm_cos_sin(float a) {  // (cos a, sin a)
     double s, c;
     sincos((double)a, &s, &c);
-    *sn = (float)s;
-    *cs = (float)c;
+    return V2{(float)c, (float)s};
 }
 
 // Rust `as u32` (saturating) and num-traits `to_u32().unwrap_or(1)`

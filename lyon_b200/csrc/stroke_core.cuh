@@ -459,6 +459,9 @@ LYC_HD void compute_join_fw(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const St
         }
     }
 }
+LYC_NOINLINE void compute_join_fw_nl(Join& j, V2 pp, V2 pj, V2 pn, bool join_fs, const StrokeParams& o) {
+    compute_join_fw(j, pp, pj, pn, join_fs, o);
+}
 // Vertex ids of a join whose first vertex is `base`, in add_stroke_vertex order:
 // fast path Positive then Negative (stroke.rs:1791-1797); otherwise Negative side then Positive side,
 // each one vertex (single) or two (prev, next) (stroke.rs:1595-1608, 2024-2055).
@@ -545,11 +548,7 @@ LYC_HD ArcNode arc_node(float a0, float a1, uint32_t va, uint32_t vb, uint32_t t
     n.idb = idb;
     return n;
 }
-LYC_HD V2 arc_normal(float mid) {  // vector(mid.cos(), mid.sin()), stroke.rs:2627
-    float sn, cs;
-    libm_sincos(mid, &sn, &cs);
-    return v2(cs, sn);
-}
+LYC_HD V2 arc_normal(float mid) { return libm_cos_sin(mid); }  // vector(mid.cos(), mid.sin()), stroke.rs:2627
 struct EmitSink {
     GpuVertex* vtx;  // first vertex owned by this slot (global memory, or the shared-memory staging window)
     uint32_t* idx;   // first index owned by this slot
@@ -582,16 +581,29 @@ struct EmitSink {
         d[2] = c;
         nt++;
     }
-    LYC_HD void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb, uint32_t total) {
-        const uint32_t first_id = base + nv;
-        for (uint32_t j = 0; j < total; ++j) {
-            ArcNode n = arc_node(a0, a1, va, vb, total, first_id, j);
-            add_vertex(vt, arc_normal(n.mid), negative);
-            add_triangle(n.ida, n.id, n.idb);
-        }
-    }
+    LYC_HD void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb, uint32_t total);
     static const bool kCounting = false;
 };
+
+// All vertices and triangles of one arc, written at vtx[0..total) / idx[0..3*total) (one copy of this code per kernel).
+LYC_NOINLINE void arc_emit_nl(GpuVertex* vtx, uint32_t* idx, uint32_t first_id, VertexTemplate vt, bool negative, float a0,
+                              float a1, uint32_t va, uint32_t vb, uint32_t total) {
+    EmitSink s;
+    s.vtx = vtx;
+    s.idx = idx;
+    s.nv = s.nt = 0u;
+    s.base = first_id;
+    for (uint32_t j = 0; j < total; ++j) {
+        ArcNode n = arc_node(a0, a1, va, vb, total, first_id, j);
+        s.add_vertex(vt, arc_normal(n.mid), negative);
+        s.add_triangle(n.ida, n.id, n.idb);
+    }
+}
+LYC_HD void EmitSink::arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb, uint32_t total) {
+    arc_emit_nl(vtx + nv, idx + 3u * (size_t)nt, base + nv, vt, negative, a0, a1, va, vb, total);
+    nv += total;
+    nt += total;
+}
 
 // stroke.rs:1869-1904.  (ids of p0 after its join, ids of p1 before its join, with the fold remaps)
 template <class Sink>
@@ -734,6 +746,22 @@ LYC_HD void tessellate_round_cap(Sink& sink, VertexTemplate vt, V2 center, float
     emit_arc(sink, vt, first_side_positive, mid_angle, end_angle, mid_vertex, end_vertex, k);
 }
 
+// Out-of-line entry points used by everything `end()` emits (one End slot per sub-path: few, heavy).
+template <class Sink>
+LYC_NOINLINE void tessellate_join_nl(Sink& sink, const VertexTemplate& vt, const Join& j, const StrokeParams& o) {
+    tessellate_join(sink, vt, j, o);
+}
+template <class Sink>
+LYC_NOINLINE void emit_join_vertices_nl(Sink& sink, const VertexTemplate& vt, Join& j) {
+    emit_join_vertices(sink, vt, j);
+}
+template <class Sink>
+LYC_NOINLINE void tessellate_round_cap_nl(Sink& sink, VertexTemplate vt, V2 center, float radius, V2 start_normal,
+                                          uint32_t start_vertex, uint32_t end_vertex, V2 edge_normal, bool is_start,
+                                          const StrokeParams& o) {
+    tessellate_round_cap(sink, vt, center, radius, start_normal, start_vertex, end_vertex, edge_normal, is_start, o);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Slot neighbourhood helpers (W = Views or TileViews)
 // ---------------------------------------------------------------------------------------------------------
@@ -765,6 +793,10 @@ LYC_HD VertexTemplate slot_vertex_template(const W& w, const StrokeParams& o, ui
 template <class W>
 LYC_HD void stream_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, Join& j) {
     compute_join_fw(j, w.P(pk), w.P(s), w.P(nk), (w.F(s) & SEG_FS_BIT) != 0u, o);
+}
+template <class W>
+LYC_HD void stream_join_nl(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, Join& j) {
+    compute_join_fw_nl(j, w.P(pk), w.P(s), w.P(nk), (w.F(s) & SEG_FS_BIT) != 0u, o);
 }
 // Base vertex id of slot s. Counting pass: ids are never compared across slots in a way that matters for
 // fixed width, any distinct bases do.
@@ -919,14 +951,14 @@ LYC_HD void tessellate_empty_cap(Sink& sink, VertexTemplate vt, const StrokePara
         float radius = vt.half_width;
         uint32_t left_id = sink.add_vertex(vt, v2(-1.0f, 0.0f), false);
         uint32_t right_id = sink.add_vertex(vt, v2(1.0f, 0.0f), true);
-        tessellate_round_cap(sink, vt, c, radius, v2(-1.0f, 0.0f), left_id, right_id, v2(0.0f, 1.0f), true, o);
-        tessellate_round_cap(sink, vt, c, radius, v2(1.0f, 0.0f), right_id, left_id, v2(0.0f, -1.0f), false, o);
+        tessellate_round_cap_nl(sink, vt, c, radius, v2(-1.0f, 0.0f), left_id, right_id, v2(0.0f, 1.0f), true, o);
+        tessellate_round_cap_nl(sink, vt, c, radius, v2(1.0f, 0.0f), right_id, left_id, v2(0.0f, -1.0f), false, o);
     }
 }
 
 // One end of an open sub-path: the side position clipped against the cap line in f64
 // (tessellate_last_edge / tessellate_first_edge, stroke.rs:2160-2180, 2235-2255).
-LYC_HD V2 clip_cap_side(uint8_t cap, V2 end_point, V2 other_point, V2 side_position, V2 towards, float hw) {
+LYC_NOINLINE V2 clip_cap_side(uint8_t cap, V2 end_point, V2 other_point, V2 side_position, V2 towards, float hw) {
     if (cap == CAP_SQUARE || cap == CAP_BUTT) {
         float clip = cap == CAP_SQUARE ? hw : 0.0f;
         V2 normal = normalize(end_point - other_point);
@@ -973,7 +1005,7 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
             j0.prev_v[0] = j0.prev_v[1] = j0.next_v[0] = j0.next_v[1] = 0xFFFFFFFFu;
         } else {
             uint32_t s_l3 = prev_kept(w, s_l2);
-            stream_join(w, o, s_l2, s_l3, s_l1, j0);
+            stream_join_nl(w, o, s_l2, s_l3, s_l1, j0);
             join_assign_ids(j0, slot_vertex_base<Sink>(w, s_l2, global_base));
         }
         // p1 = last point: side points from the edge direction (stroke.rs:1338-1346)
@@ -994,7 +1026,7 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
         p1_prev_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (p1_prev[SIDE_NEGATIVE] - pl1) / hw, true);
         if (m > 2u) add_edge_triangles(sink, j0.prev_v, j0.next_v, j0.fold, p1_prev_v, p1_prev_v, no_fold);
         if (o.end_cap == CAP_ROUND)
-            tessellate_round_cap(sink, vt, pl1, hw, p1_prev[SIDE_POSITIVE] - pl1, p1_prev_v[SIDE_POSITIVE],
+            tessellate_round_cap_nl(sink, vt, pl1, hw, p1_prev[SIDE_POSITIVE] - pl1, p1_prev_v[SIDE_POSITIVE],
                                  p1_prev_v[SIDE_NEGATIVE], v, false, o);
         // tessellate_first_edge (stroke.rs:2208-2276): first = P0, second = P1 (firsts[1] when count > 2)
         V2 first_next[2];
@@ -1010,7 +1042,7 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
         } else {
             uint32_t s_p2 = next_kept_or_end(w, s_p1);
             Join j1;
-            stream_join(w, o, s_p1, b0, s_p2, j1);
+            stream_join_nl(w, o, s_p1, b0, s_p2, j1);
             join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
             second_prev[0] = j1.prev[0];
             second_prev[1] = j1.prev[1];
@@ -1034,7 +1066,7 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
             add_edge_triangles(sink, unset, first_next_v, no_fold, second_prev_v, second_next_v, second_fold);
         }
         if (o.start_cap == CAP_ROUND)
-            tessellate_round_cap(sink, vf, P0, hw, first_next[SIDE_NEGATIVE] - P0, first_next_v[SIDE_NEGATIVE],
+            tessellate_round_cap_nl(sink, vf, P0, hw, first_next[SIDE_NEGATIVE] - P0, first_next_v[SIDE_NEGATIVE],
                                  first_next_v[SIDE_POSITIVE], P0 - P1, true, o);
         return;
     }
@@ -1043,13 +1075,13 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
     // firsts[0] = P0 (advancement reset to NaN), firsts[1] = P1 with the state of its stream join.
     uint32_t s_p2 = next_kept_or_end(w, s_p1);
     Join j1;  // firsts[1]
-    stream_join(w, o, s_p1, b0, s_p2, j1);
+    stream_join_nl(w, o, s_p1, b0, s_p2, j1);
     join_assign_ids(j1, slot_vertex_base<Sink>(w, s_p1, global_base));
     const float start_advancement = w.A(b0);
     V2 A = w.P(s_l2), B = w.P(s_l1);
     uint32_t s_l3 = prev_kept(w, s_l2);  // exists: m > 2
     Join ja;                             // join at A = second to last kept point (already emitted by its slot)
-    stream_join(w, o, s_l2, s_l3, s_l1, ja);
+    stream_join_nl(w, o, s_l2, s_l3, s_l1, ja);
     join_assign_ids(ja, slot_vertex_base<Sink>(w, s_l2, global_base));
     const bool b_fs = (w.F(s_l1) & SEG_FS_BIT) != 0u;
 
@@ -1059,29 +1091,29 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
     if (segment_added) {
         // step(P0'): join at B between A and P0
         Join jb;
-        compute_join_fw(jb, A, B, P0, b_fs, o);
+        compute_join_fw_nl(jb, A, B, P0, b_fs, o);
         VertexTemplate vb = slot_vertex_template(w, o, s_l1);
-        emit_join_vertices(sink, vb, jb);
+        emit_join_vertices_nl(sink, vb, jb);
         add_edge_triangles(sink, ja, jb);
-        tessellate_join(sink, vb, jb, o);
+        tessellate_join_nl(sink, vb, jb, o);
         // step(P1'): join at P0' between B and P1; P0' is never a flattening step
-        compute_join_fw(jc, B, P0, P1, false, o);
+        compute_join_fw_nl(jc, B, P0, P1, false, o);
         vc = slot_vertex_template(w, o, b0);
         vc.advancement = vb.advancement + length(P0 - B);
-        emit_join_vertices(sink, vc, jc);
+        emit_join_vertices_nl(sink, vc, jc);
         add_edge_triangles(sink, jb, jc);
-        tessellate_join(sink, vc, jc, o);
+        tessellate_join_nl(sink, vc, jc, o);
     } else {
         // The closing point merged into B: B takes P0's position (stroke.rs:1228-1238), then step(P1').
-        compute_join_fw(jc, A, P0, P1, b_fs, o);
+        compute_join_fw_nl(jc, A, P0, P1, b_fs, o);
         vc = slot_vertex_template(w, o, s_l1);
         vc.position_on_path = P0;
         // B's advancement was already fixed iff the join at A took the fast path (flattened_step sets
         // next.advancement, stroke.rs:1765-1769); otherwise it is computed now from the moved position.
         if (!ja.fast) vc.advancement = w.A(s_l2) + length(P0 - A);
-        emit_join_vertices(sink, vc, jc);
+        emit_join_vertices_nl(sink, vc, jc);
         add_edge_triangles(sink, ja, jc);
-        tessellate_join(sink, vc, jc, o);
+        tessellate_join_nl(sink, vc, jc, o);
     }
     // Re-create the two vertices towards the second endpoint with the sub-path start advancement (stroke.rs:1248-1275)
     vc.advancement = start_advancement;

@@ -189,37 +189,55 @@ LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t s
     float* len = w.len();
     uint32_t s = sa;
     while (s < sb) {
-        if ((s & 3u) == 0u && s + 32u <= sb && m >= 1u && last_kept == s - 1u) {
-            // special bits of slots [s, s + 32)
-            const uint32_t sh = s & 31u;
-            uint32_t bits = special[s >> 5] >> sh;
-            if (sh) bits |= special[(s >> 5) + 1u] << (32u - sh);
-            if (bits == 0u) {
 #ifdef __CUDA_ARCH__
-                const float4* l4 = reinterpret_cast<const float4*>(len + s);
-                float4* a4 = reinterpret_cast<float4*>(w.adv + s);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 l = l4[q];
+        // A run of ordinary points: the bare f32 addition chain, four slots (one 16-byte load / store) at a time.  The
+        // next quad's lengths are loaded before this quad's results are stored (the arrays may alias as far as the
+        // compiler knows), so the loads stay off the dependent chain.
+        if ((s & 3u) == 0u && s + 4u <= sb && m >= 1u && last_kept == s - 1u) {
+            uint32_t word = special[s >> 5] >> (s & 31u);
+            uint32_t left = 32u - (s & 31u);
+            if ((word & 0xFu) == 0u) {
+                float4 l = *reinterpret_cast<const float4*>(len + s);
+                const uint32_t s_in = s;
+                for (;;) {
+                    const uint32_t s2 = s + 4u;
+                    bool more = false;
+                    float4 ln = l;
+                    if (s2 + 4u <= sb) {
+                        word >>= 4;
+                        left -= 4u;
+                        if (left == 0u) {
+                            word = special[s2 >> 5];
+                            left = 32u;
+                        }
+                        more = (word & 0xFu) == 0u;
+                        ln = *reinterpret_cast<const float4*>(len + s2);
+                    }
                     float4 a;
                     a.x = adv = adv + l.x;
                     a.y = adv = adv + l.y;
                     a.z = adv = adv + l.z;
                     a.w = adv = adv + l.w;
-                    a4[q] = a;
+                    *reinterpret_cast<float4*>(w.adv + s) = a;
+                    s = s2;
+                    if (!more) break;
+                    l = ln;
                 }
-#else
-                for (uint32_t q = 0; q < 32u; ++q) {
-                    adv = adv + len[s + q];
-                    w.adv[s + q] = adv;
-                }
-#endif
-                m += 32u;
-                last_kept = s + 31u;
-                s += 32u;
+                m += s - s_in;
+                last_kept = s - 1u;
                 continue;
             }
         }
+#else
+        if (m >= 1u && last_kept == s - 1u && !((special[s >> 5] >> (s & 31u)) & 1u)) {
+            adv = adv + len[s];
+            w.adv[s] = adv;
+            m++;
+            last_kept = s;
+            ++s;
+            continue;
+        }
+#endif
         const uint8_t fl = w.flags[s];
         if (fl & TF_BEGIN) {
             begin_slot = s;
