@@ -605,7 +605,7 @@ struct lyon_cuda_ctx {
     size_t max_smem_optin = 0;
     Totals* h_totals = nullptr;  // pinned
     // fused tile pipeline
-    DevBuf path_slots, path_events, path_slot_begin, path_event_begin, tile_first, tile_desc, tile_base, tile_misc;
+    DevBuf verb_n, path_slots, path_events, path_slot_begin, path_event_begin, tile_first, tile_desc, tile_base, tile_misc;
     TileTotals* h_tile_totals = nullptr;  // pinned
     bool tile_planned = false;            // the last plan went through the tile pipeline
     lyon_path_batch tile_batch{};
@@ -784,6 +784,7 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     *usable = false;
     if (c->tile_force_general || !b->path_point_begin || b->n_paths == 0 || b->n_verbs == 0) return LYON_OK;
     const uint32_t np = b->n_paths;
+    TRY(ensure(c, c->verb_n, ((size_t)b->n_verbs + 1) * 4));
     TRY(ensure(c, c->path_slots, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->path_events, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->path_slot_begin, ((size_t)np + 1) * 8));
@@ -798,7 +799,7 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
     k_path_slots<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
                                                b->path_point_begin, np, c->params, (uint32_t*)c->path_slots.p,
-                                               (uint32_t*)c->path_events.p, d_tile_totals(c));
+                                               (uint32_t*)c->path_events.p, (float*)c->verb_n.p, d_tile_totals(c));
     k_scan_paths<<<ptiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->path_slots.p, (const uint32_t*)c->path_events.p, np,
                                                  (unsigned long long*)c->path_slot_begin.p, (uint32_t*)c->path_event_begin.p,
                                                  d_tile_ticket(c, 0), (uint64_t*)c->tile_desc.p,
@@ -868,6 +869,7 @@ int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, ui
     TileArgs a{};
     a.verbs = b.verbs;
     a.points = reinterpret_cast<const V2*>(b.points);
+    a.verb_n = (const float*)c->verb_n.p;
     a.path_verb_begin = b.path_verb_begin;
     a.path_point_begin = b.path_point_begin;
     a.path_slot_begin = (const unsigned long long*)c->path_slot_begin.p;
@@ -892,7 +894,11 @@ int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, ui
     a.path_vertex_end = (unsigned long long*)d_path_vertex_end;
     a.path_index_end = (unsigned long long*)d_path_index_end;
 #ifdef LYON_DEV_BUILD  // experiments only: one instantiation, compiles 4x faster
-    return tile_launch_nt<256, MODE, 2>(c, a);
+#ifndef LYON_DEV_NT
+#define LYON_DEV_NT 256
+#define LYON_DEV_MINB 2
+#endif
+    return tile_launch_nt<LYON_DEV_NT, MODE, LYON_DEV_MINB>(c, a);
 #else
     switch (c->tile_nt) {
         case 128: return tile_launch_nt<128, MODE, 4>(c, a);
@@ -952,7 +958,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
-                      &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
+                      &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);

@@ -94,81 +94,87 @@ LYC_HD uint32_t tile_gen_quad_half(const TileViews& w, const StrokeParams& p, ui
 }
 
 // Phase 1a (thread per verb): every slot of verb `verb` (first stored point `pt`, first slot s0, EndpointId `src`).
-// Single-slot verbs and the rare split quadratics are finished here.  For ordinary curves only the SEQUENTIAL part
-// runs here -- the accumulated parameter t1 = t0 + step of for_each_flattened_with_t (cubic_bezier.rs:605-611,
-// quadratic_bezier.rs:382-388) -- and each slot is left marked TF_EVAL with the verb's point index parked in `adv`;
-// phase 1b evaluates the positions with one thread per slot (no divergence between curves of different counts).
+// Only the SEQUENTIAL part of a verb runs here -- the accumulated parameter t1 = t0 + step of
+// for_each_flattened_with_t (cubic_bezier.rs:605-611, quadratic_bezier.rs:382-388) -- and every slot is left with its
+// kind in the low flag bits and the verb's point index parked in `adv`; phase 1b computes positions and edge lengths
+// with one thread per slot (no divergence between verbs of different kinds and counts).  Low flag bits for phase 1b:
+//   TF_EVAL [| TF_CUBIC] [| TF_FIRST] [| TF_LAST]   curve sample        TF_CUBIC alone   line endpoint
+//   TF_BEGIN / TF_END (high bits)                    Begin / End slot    none             finished here (split quadratic)
+// The rare quadratics split by flatten_quad (stroke.rs:2755-2779) are finished here.
 LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t verb, const V2* points, uint32_t pt,
                           const VerbPlan& plan, uint32_t s0, uint32_t src) {
     const uint32_t a = p.attr_stride;
+    if (verb == VERB_QUAD && plan.tsplit >= 0.0f) {
+        const V2 from = seg_from_point(points, pt, a);
+        const V2 ctrl = points[pt], to = points[pt + 1];
+        const float ts = plan.tsplit;
+        const V2 sp = quad_sample(from, ctrl, to, ts);
+        uint32_t n1 = tile_gen_quad_half(w, p, s0, from, lerp(from, ctrl, ts), sp, plan.n_a, true, ts, src, 0);
+        tile_gen_quad_half(w, p, s0 + n1, sp, lerp(ctrl, to, ts), to, plan.n_b, false, ts, src, 0);
+        return;
+    }
+    const bool curve = verb == VERB_CUBIC || verb == VERB_QUAD;
+    const uint32_t cnt = curve ? to_u32_or_1(plan.n_a) : 1u;
+    const float step = curve ? 1.0f / plan.n_a : 0.0f;
+    uint8_t kind;
     switch (verb) {
-        case VERB_BEGIN:
-            tile_put_slot(w, p, s0, points[pt], v2(0.0f, 0.0f), false, 1.0f, TF_BEGIN, src);
-            break;
-        case VERB_LINE:
-            tile_put_slot(w, p, s0, points[pt], seg_from_point(points, pt, a), true, 1.0f, TF_FIRST, src);
-            break;
-        case VERB_CUBIC:
-        case VERB_QUAD: {
-            if (verb == VERB_QUAD && plan.tsplit >= 0.0f) {
-                const V2 from = seg_from_point(points, pt, a);
-                const V2 ctrl = points[pt], to = points[pt + 1];
-                const float ts = plan.tsplit;
-                const V2 sp = quad_sample(from, ctrl, to, ts);
-                uint32_t n1 = tile_gen_quad_half(w, p, s0, from, lerp(from, ctrl, ts), sp, plan.n_a, true, ts, src, TF_FIRST);
-                tile_gen_quad_half(w, p, s0 + n1, sp, lerp(ctrl, to, ts), to, plan.n_b, false, ts, src, 0);
-                break;
-            }
-            const float step = 1.0f / plan.n_a;
-            const uint32_t cnt = to_u32_or_1(plan.n_a);
-            const uint8_t kind = TF_EVAL | (verb == VERB_CUBIC ? TF_CUBIC : 0);
-            const float ptbits = u2f(pt);
-            float t = 0.0f;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                float ts = 1.0f;
-                if (k + 1u < cnt) {
-                    t = t + step;
-                    ts = t;
-                }
-                w.t[s0 + k] = ts;
-                w.flags[s0 + k] = kind | (ts != 1.0f ? TF_FS : 0) | (k == 0u ? TF_FIRST : 0) | (k + 1u < cnt ? 0 : TF_LAST);
-                w.src[s0 + k] = src;
-                w.adv[s0 + k] = ptbits;
-            }
-            break;
+        case VERB_BEGIN: kind = TF_BEGIN; break;
+        case VERB_LINE: kind = TF_CUBIC; break;
+        case VERB_CUBIC: kind = TF_EVAL | TF_CUBIC; break;
+        case VERB_QUAD: kind = TF_EVAL; break;
+        case VERB_CLOSE: kind = TF_END | TF_CLOSE; break;
+        default: kind = TF_END; break;
+    }
+    const float ptbits = u2f(pt);
+    float t = 0.0f;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        float ts = 1.0f;
+        if (k + 1u < cnt) {
+            t = t + step;
+            ts = t;
         }
-        default:  // End / Close: not a point; pos/adv are written by tile_path_walk (sub-path record)
-            w.flags[s0] = TF_END | (verb == VERB_CLOSE ? TF_CLOSE : 0);
-            w.t[s0] = 1.0f;
-            w.src[s0] = 0u;
-            w.len()[s0] = 0.0f;
-            break;
+        uint8_t fl = kind;
+        if (curve) fl |= (ts != 1.0f ? TF_FS : 0) | (k == 0u ? TF_FIRST : 0) | (k + 1u < cnt ? 0 : TF_LAST);
+        w.t[s0 + k] = ts;
+        w.flags[s0 + k] = fl;
+        w.src[s0 + k] = src;
+        w.adv[s0 + k] = ptbits;
     }
 }
 
-// Phase 1b (thread per slot): position of a TF_EVAL slot from its t (polynomial form, cubic_bezier.rs:1318-1365 /
-// quadratic_bezier.rs:891-939; the last point of a curve is the exact endpoint) and its distance to the previous fed
-// point (the previous sample of the same curve is re-evaluated rather than read, so the phase needs no ordering).
+// Phase 1b (thread per slot): position of a slot and its distance to the previous fed point.  Curve samples come from
+// the polynomial form (cubic_bezier.rs:1318-1365 / quadratic_bezier.rs:891-939; the last point of a curve is the exact
+// endpoint); the previous sample of the same curve is re-evaluated rather than read, so the phase needs no ordering.
 LYC_HD void tile_eval_slot(const TileViews& w, const StrokeParams& p, const V2* points, uint32_t s) {
     const uint8_t fl = w.flags[s];
-    if (!(fl & TF_EVAL)) return;
     const uint32_t pt = f2u(w.adv[s]);
-    const float t = w.t[s];
-    const V2 from = seg_from_point(points, pt, p.attr_stride);
-    V2 pos, prev;
-    if (fl & TF_CUBIC) {
-        const V2 to = points[pt + 2];
-        const CubicPoly poly = cubic_poly(from, points[pt], points[pt + 1], to);
-        pos = (fl & TF_LAST) ? to : cubic_poly_sample(poly, t);
-        prev = (fl & TF_FIRST) ? from : cubic_poly_sample(poly, w.t[s - 1u]);
-    } else {
-        const V2 to = points[pt + 1];
-        const QuadPoly poly = quad_poly(from, points[pt], to);
-        pos = (fl & TF_LAST) ? to : quad_poly_sample(poly, t);
-        prev = (fl & TF_FIRST) ? from : quad_poly_sample(poly, w.t[s - 1u]);
+    if (fl & TF_EVAL) {
+        const float t = w.t[s];
+        const V2 from = seg_from_point(points, pt, p.attr_stride);
+        V2 pos, prev;
+        if (fl & TF_CUBIC) {
+            const V2 to = points[pt + 2];
+            const CubicPoly poly = cubic_poly(from, points[pt], points[pt + 1], to);
+            pos = (fl & TF_LAST) ? to : cubic_poly_sample(poly, t);
+            prev = (fl & TF_FIRST) ? from : cubic_poly_sample(poly, w.t[s - 1u]);
+        } else {
+            const V2 to = points[pt + 1];
+            const QuadPoly poly = quad_poly(from, points[pt], to);
+            pos = (fl & TF_LAST) ? to : quad_poly_sample(poly, t);
+            prev = (fl & TF_FIRST) ? from : quad_poly_sample(poly, w.t[s - 1u]);
+        }
+        w.pos[s] = pos;
+        w.len()[s] = tile_len_flagged(p, pos, prev);
+    } else if (fl & TF_BEGIN) {
+        w.pos[s] = points[pt];
+        w.len()[s] = 0.0f;
+    } else if (fl & TF_END) {
+        w.len()[s] = 0.0f;  // pos/adv are written by tile_path_walk (sub-path record)
+    } else if (fl & TF_CUBIC) {  // line endpoint
+        const V2 pos = points[pt];
+        w.pos[s] = pos;
+        w.len()[s] = tile_len_flagged(p, pos, seg_from_point(points, pt, p.attr_stride));
     }
-    w.pos[s] = pos;
-    w.len()[s] = tile_len_flagged(p, pos, prev);
 }
 // Phase 1c: a slot is "special" for the walk when it is not an ordinary kept point: Begin, End, or possibly within
 // the merge distance of its predecessor.

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 import workloads as W  # noqa: E402
 from lyon_b200 import DeviceTessellator, LineCap, LineJoin, StrokeOptions  # noqa: E402
 
-NAMES = ["0 ticket", "1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
+NAMES = ["0 ticket", "0 stage + 1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
          "6 fast emit", "6 full/end emit"]
 
 
@@ -36,10 +36,12 @@ def main():
     torch.cuda.synchronize()
     ms = tz.last_kernel_ms()
     tz.L.lyon_cuda_debug_phase_cycles(tz.ctx, out)
-    tot = sum(out)
+    tot = sum(out[:11])
     print(f"paths {n} vertices {v.shape[0]} kernel {ms:.3f} ms")
     for k, name in enumerate(NAMES):
         print(f"  {name:18s} {out[k] / tot * 100:6.2f} %   {out[k]:>14d} cycles")
+    if out[12] and out[14]:
+        print(f"  emit loop per warp: joins {out[11] / out[12]:.0f} cycles ({out[12]} warps), Ends {out[13] / out[14]:.0f} cycles ({out[14]} warps)")
 
 
 if __name__ == "__main__":
