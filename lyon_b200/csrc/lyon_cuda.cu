@@ -22,6 +22,7 @@
 
 #include "../../include/lyon_cuda.h"
 #include "stroke_tile.cuh"
+#include "stroke_vw.cuh"
 
 using namespace lyc;
 
@@ -581,6 +582,87 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variable line width (stroke_vw.cuh): one thread per path runs the streaming state machine, once to count, once to emit.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_vw_count(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+                                                  const uint32_t* __restrict__ path_verb_begin,
+                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, StrokeParams p,
+                                                  uint32_t* __restrict__ path_nv, uint32_t* __restrict__ path_nt) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n_paths) return;
+    CountSink sink;
+    sink.nv = sink.nt = 0u;
+    sink.base = 0u;
+    vw_stroke_path(verbs, path_verb_begin[path], path_verb_begin[path + 1], points, path_point_begin[path], p, sink);
+    path_nv[path] = sink.nv;
+    path_nt[path] = sink.nt;
+}
+// Exclusive scan of u32 counts into u64 offsets (n + 1 entries), decoupled look-back over tiles of BLOCK * 4 items.
+__global__ void __launch_bounds__(BLOCK) k_scan_counts(const uint32_t* __restrict__ in, uint32_t n,
+                                                       unsigned long long* __restrict__ out, uint32_t* ticket, uint64_t* desc) {
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base, s_sum[WARPS];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t i0 = (tile * BLOCK + threadIdx.x) * 4u;
+    uint32_t x[4];
+    unsigned long long sum = 0ull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+        sum += x[k];
+    }
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += y;
+    }
+    if (lane == 31u) s_sum[wid] = inc;
+    __syncthreads();
+    unsigned long long wbase = 0ull, agg = 0ull;
+    for (int k = 0; k < WARPS; ++k) {
+        if (k < (int)wid) wbase += s_sum[k];
+        agg += s_sum[k];
+    }
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_exclusive(desc, tile, agg);
+        if (threadIdx.x == 0) s_base = e;
+    }
+    __syncthreads();
+    unsigned long long run = s_base + wbase + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += x[k];
+        if (i0 + k + 1 == n) out[n] = run;
+    }
+}
+__global__ void __launch_bounds__(128) k_vw_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+                                                 const uint32_t* __restrict__ path_verb_begin,
+                                                 const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, StrokeParams p,
+                                                 const unsigned long long* __restrict__ path_v0,
+                                                 const unsigned long long* __restrict__ path_t0, GpuVertex* __restrict__ vertices,
+                                                 uint32_t* __restrict__ indices, uint32_t vertex_base,
+                                                 unsigned long long* __restrict__ path_vertex_end,
+                                                 unsigned long long* __restrict__ path_index_end, Totals* totals) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n_paths) return;
+    const unsigned long long v0 = path_v0[path], t0 = path_t0[path];
+    EmitSink sink;
+    sink.vtx = vertices + v0;
+    sink.idx = indices + 3ull * t0;
+    sink.nv = sink.nt = 0u;
+    sink.base = vertex_base + (uint32_t)v0;
+    vw_stroke_path(verbs, path_verb_begin[path], path_verb_begin[path + 1], points, path_point_begin[path], p, sink);
+    if (sink.nv != path_v0[path + 1] - v0 || sink.nt != path_t0[path + 1] - t0) atomicOr(&totals->error, 1u);
+    if (path_vertex_end) path_vertex_end[path] = v0 + sink.nv;
+    if (path_index_end) path_index_end[path] = 3ull * (t0 + sink.nt);
+}
+
 #include "tile_kernels.cuh"
 
 }  // namespace
@@ -608,6 +690,9 @@ struct lyon_cuda_ctx {
     DevBuf verb_n, path_slots, path_events, path_slot_begin, path_event_begin, tile_first, tile_desc, tile_base, tile_misc;
     TileTotals* h_tile_totals = nullptr;  // pinned
     bool tile_planned = false;            // the last plan went through the tile pipeline
+    bool vw_planned = false;              // the last plan went through the variable-width (thread per path) kernels
+    DevBuf vw_nv, vw_nt, vw_v0, vw_t0;
+    lyon_path_batch vw_batch{};
     lyon_path_batch tile_batch{};
     uint32_t tile_n_tiles = 0, tile_s_cap = 0, tile_w_v = 0, tile_w_t = 0, tile_quantum = 0;
     int tile_nt = 256;
@@ -918,6 +1003,76 @@ int tile_error(lyon_cuda_ctx* c) {
     return LYON_OK;
 }
 
+// Variable line width: count per path, scan, (later) emit.  See stroke_vw.cuh.
+int vw_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t* n_vertices, uint64_t* n_indices) {
+    if ((uint32_t)o->variable_line_width >= b->num_attributes) return LYON_ERR_INVALID_ARGUMENT;
+    c->n_paths = b->n_paths;
+    c->n_vertices = c->n_triangles = 0;
+    c->d_path_verb_begin = b->path_verb_begin;
+    c->params = make_params(*o, b->num_attributes);
+    c->views = Views{};
+    c->tile_planned = false;
+    if (b->n_verbs == 0 || b->n_paths == 0) {
+        c->planned = true;
+        return LYON_OK;
+    }
+    if (!b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
+    const uint32_t np = b->n_paths;
+    TRY(ensure(c, c->vw_nv, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->vw_nt, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->vw_v0, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->vw_t0, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->misc, 512));
+    const unsigned tiles = grid_for(np, BLOCK * 4);
+    TRY(ensure(c, c->desc, (size_t)tiles * 16));
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 16, c->stream));
+    if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    k_vw_count<<<grid_for(np, 128), 128, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
+                                                        b->path_point_begin, np, c->params, (uint32_t*)c->vw_nv.p,
+                                                        (uint32_t*)c->vw_nt.p);
+    if (c->timing) {
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+    }
+    k_scan_counts<<<tiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, np, (unsigned long long*)c->vw_v0.p, d_ticket(c, 0),
+                                                 (uint64_t*)c->desc.p);
+    k_scan_counts<<<tiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nt.p, np, (unsigned long long*)c->vw_t0.p, d_ticket(c, 1),
+                                                 (uint64_t*)c->desc.p + tiles);
+    c->launches += 3;
+    CU_TRY(c, cudaGetLastError());
+    unsigned long long tot[2] = {0ull, 0ull};
+    CU_TRY(c, cudaMemcpyAsync(&tot[0], (unsigned long long*)c->vw_v0.p + np, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&tot[1], (unsigned long long*)c->vw_t0.p + np, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->n_vertices = tot[0];
+    c->n_triangles = tot[1];
+    if (c->n_vertices > 0xFFFFFFFFull || c->n_triangles > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+    *n_vertices = c->n_vertices;
+    *n_indices = 3ull * c->n_triangles;
+    c->vw_batch = *b;
+    c->vw_planned = true;
+    c->planned = true;
+    return LYON_OK;
+}
+int vw_emit(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, uint64_t vertex_base, uint64_t* d_path_vertex_end,
+            uint64_t* d_path_index_end) {
+    const lyon_path_batch& b = c->vw_batch;
+    if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+    if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    k_vw_emit<<<grid_for(b.n_paths, 128), 128, 0, c->stream>>>(
+        b.verbs, reinterpret_cast<const V2*>(b.points), b.path_verb_begin, b.path_point_begin, b.n_paths, c->params,
+        (const unsigned long long*)c->vw_v0.p, (const unsigned long long*)c->vw_t0.p, d_vertices, d_indices, (uint32_t)vertex_base,
+        (unsigned long long*)d_path_vertex_end, (unsigned long long*)d_path_index_end, d_totals(c));
+    if (c->timing) {
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -958,7 +1113,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
-                      &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
+                      &c->vw_nv, &c->vw_nt, &c->vw_v0, &c->vw_t0, &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -1007,10 +1162,8 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
     c->planned = false;
     if (o->tolerance != o->tolerance) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN
     if (o->start_cap > 2 || o->end_cap > 2 || o->line_join > 3) return LYON_ERR_INVALID_ARGUMENT;
-    if (o->variable_line_width >= 0 && b->num_attributes > 0) {
-        c->err = "variable_line_width is not implemented on the device yet";
-        return LYON_ERR_UNSUPPORTED_PARAMETER;
-    }
+    c->vw_planned = false;
+    if (o->variable_line_width >= 0 && b->num_attributes > 0) return vw_plan(c, b, o, n_vertices, n_indices);
     if (b->n_verbs >= SEG_MASK) return LYON_ERR_INVALID_ARGUMENT;
     c->n_paths = b->n_paths;
     c->n_vertices = c->n_triangles = 0;
@@ -1125,6 +1278,7 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
     }
     // ids handed out are vertex_base .. vertex_base + V - 1 and must be <= u32::MAX - 1 (geometry_builder.rs:342-346)
     if (c->n_vertices && vertex_base + c->n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (c->vw_planned) return vw_emit(c, (GpuVertex*)d_vertices, d_indices, vertex_base, d_path_vertex_end, d_path_index_end);
     if (c->tile_planned) {
         if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
         return tile_launch<TILE_MODE_EMIT>(c, (GpuVertex*)d_vertices, d_indices, c->n_vertices, c->n_triangles, vertex_base,
@@ -1210,13 +1364,10 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyo
     c->tile_planned = false;
     if (o->tolerance != o->tolerance) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN
     if (o->start_cap > 2 || o->end_cap > 2 || o->line_join > 3) return LYON_ERR_INVALID_ARGUMENT;
-    if (o->variable_line_width >= 0 && b->num_attributes > 0) {
-        c->err = "variable_line_width is not implemented on the device yet";
-        return LYON_ERR_UNSUPPORTED_PARAMETER;
-    }
     if ((vertex_capacity && !d_vertices) || (index_capacity && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
     bool usable = false;
-    if (b->n_paths && b->n_verbs) {
+    const bool vw = o->variable_line_width >= 0 && b->num_attributes > 0;  // thread-per-path kernels: plan, then emit
+    if (!vw && b->n_paths && b->n_verbs) {
         if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
         c->params = make_params(*o, b->num_attributes);
         TRY(tile_prepass(c, b, &usable));

@@ -10,6 +10,7 @@
 
 #include "../../include/lyon_cuda.h"
 #include "../../lyon_b200/csrc/stroke_tile.cuh"
+#include "../../lyon_b200/csrc/stroke_vw.cuh"
 
 using namespace lyc;
 
@@ -286,4 +287,46 @@ extern "C" uint64_t emul_flatten(const float* ctrl, uint64_t n, int npts, float 
     }
     offsets[n] = off;
     return off;
+}
+
+// Variable line width (stroke_vw.cuh): the per-path state machine the k_vw_count / k_vw_emit threads run, paths in a loop.
+extern "C" int emul_stroke_batch_vw(const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t vertex_base,
+                                    lyon_stroke_vertex** out_v, uint64_t* n_v, uint32_t** out_i, uint64_t* n_i,
+                                    uint64_t* path_vertex_end, uint64_t* path_index_end) {
+    *out_v = nullptr;
+    *out_i = nullptr;
+    *n_v = *n_i = 0;
+    StrokeParams p = make_params(*o, b->num_attributes);
+    const V2* points = reinterpret_cast<const V2*>(b->points);
+    std::vector<uint64_t> v0(b->n_paths + 1, 0), t0(b->n_paths + 1, 0);
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        CountSink sink;
+        sink.nv = sink.nt = 0;
+        sink.base = 0;
+        vw_stroke_path(b->verbs, b->path_verb_begin[path], b->path_verb_begin[path + 1], points, b->path_point_begin[path], p, sink);
+        v0[path + 1] = v0[path] + sink.nv;
+        t0[path + 1] = t0[path] + sink.nt;
+    }
+    const uint64_t tv = v0[b->n_paths], tt = t0[b->n_paths];
+    if (tv > 0xFFFFFFFFull || tt > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (tv && vertex_base + tv - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    GpuVertex* V = (GpuVertex*)malloc((tv ? tv : 1) * sizeof(GpuVertex));
+    uint32_t* I = (uint32_t*)malloc((tt ? tt : 1) * 12);
+    int status = LYON_OK;
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        EmitSink sink;
+        sink.vtx = V + v0[path];
+        sink.idx = I + 3ull * t0[path];
+        sink.nv = sink.nt = 0;
+        sink.base = (uint32_t)vertex_base + (uint32_t)v0[path];
+        vw_stroke_path(b->verbs, b->path_verb_begin[path], b->path_verb_begin[path + 1], points, b->path_point_begin[path], p, sink);
+        if (sink.nv != v0[path + 1] - v0[path] || sink.nt != t0[path + 1] - t0[path]) status = LYON_ERR_INTERNAL;
+        if (path_vertex_end) path_vertex_end[path] = v0[path + 1];
+        if (path_index_end) path_index_end[path] = 3ull * t0[path + 1];
+    }
+    *out_v = (lyon_stroke_vertex*)V;
+    *out_i = I;
+    *n_v = tv;
+    *n_i = 3ull * tt;
+    return status;
 }

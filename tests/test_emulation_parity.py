@@ -124,6 +124,21 @@ def test_c5_tolerance_sweep(tol):
     assert_mesh_parity(E.stroke_batch(batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
 
 
+@pytest.mark.parametrize("num_attributes,attr", [(1, 0), (2, 1), (3, 2)])
+def test_variable_line_width_state_machine(num_attributes, attr):
+    """stroke_vw.cuh (the code k_vw_count / k_vw_emit run per path) against the oracle's variable-width path."""
+    batch = W.random_width_paths(120, seed=40 + num_attributes, num_attributes=num_attributes)
+    for o in all_options(0.1):
+        o = o.with_variable_line_width(attr)
+        assert_mesh_parity(E.stroke_batch(batch, o), O.stroke_batch(batch, o), 100.0)
+
+
+def test_c4_polylines_variable_width():
+    batch = W.c4_polylines(40, 300, with_attribute=True)
+    o = StrokeOptions(line_join=LineJoin.Miter, miter_limit=4.0).with_variable_line_width(0)
+    assert_mesh_parity(E.stroke_batch(batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
+
+
 def test_vertex_base_rebasing_and_overflow():
     batch = W.c3_mixed_paths(10, 8, seed=1)
     o = StrokeOptions()

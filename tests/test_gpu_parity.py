@@ -168,6 +168,29 @@ def test_c4_sample_fixed_width(tz):
     assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch))
 
 
+def test_c4_sample_variable_width(tz):
+    """C4 as BASELINE.json states it: 1k-segment polylines, miter joins with limit 4, butt caps, line width from
+    custom attribute 0 (StrokeOptions::variable_line_width) -- the thread-per-path kernels of stroke_vw.cuh."""
+    batch = W.c4_polylines(300, 1000, with_attribute=True)
+    o = StrokeOptions(line_join=LineJoin.Miter, miter_limit=4.0).with_variable_line_width(0)
+    got, pve, pie = gpu_stroke(tz, batch, o, with_ranges=True)
+    want, wpve, wpie = O.stroke_batch(batch, o, with_ranges=True)
+    assert_mesh_parity(got, want, bbox_extent(batch))
+    assert np.array_equal(pve, wpve) and np.array_equal(pie, wpie)
+
+
+@pytest.mark.parametrize("num_attributes,attr", [(1, 0), (2, 1), (3, 2)])
+def test_variable_width_adversarial_paths(tz, num_attributes, attr):
+    batch = W.random_width_paths(400, seed=70 + num_attributes, num_attributes=num_attributes)
+    for tol, w, ml in ((0.1, 1.0, 4.0), (0.02, 3.0, 2.0)):
+        for join in LineJoin:
+            for cap in LineCap:
+                o = StrokeOptions(tolerance=tol, line_width=w, line_join=join, miter_limit=ml).with_line_cap(cap)
+                o = o.with_variable_line_width(attr)
+                assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), 100.0,
+                                   what=str(o))
+
+
 @pytest.mark.parametrize("tol", [1.0, 0.3, 0.1, 0.03, 0.01, 0.003, 0.001])
 def test_c5_tolerance_sweep(tz, tol):
     batch = W.c5_logo_copies(W.fixture_paths(GOLDEN), 40)

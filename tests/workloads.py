@@ -137,6 +137,52 @@ def random_small_paths(n_paths: int, seed: int, max_segments: int = 12, closed_f
     return PathBatch.from_paths(paths)
 
 
+def random_width_paths(n_paths: int, seed: int, num_attributes: int = 1, max_segments: int = 10, closed_fraction=0.4,
+                       degenerate=0.15) -> PathBatch:
+    """Adversarial little paths with custom attributes (attribute 0.. are width factors in [0.2, 3)) for the variable
+    line width path: mixed verbs, closed/open sub-paths, duplicates, reversals, far control points."""
+    rng = np.random.default_rng(seed)
+    paths = []
+
+    def attrs():
+        return [float(np.float32(rng.uniform(0.2, 3.0))) for _ in range(num_attributes)]
+
+    for _ in range(n_paths):
+        b = Path.builder_with_attributes(num_attributes)
+        for _sp in range(int(rng.integers(1, 3))):
+            cur = rng.uniform(-50, 50, size=2).astype(np.float32)
+            b.begin(tuple(cur), attrs())
+            last_step = np.array([1.0, 0.0], np.float32)
+            for _s in range(int(rng.integers(0, max_segments + 1))):
+                r = rng.uniform()
+                if r < degenerate * 0.4:
+                    step = np.zeros(2, np.float32)
+                elif r < degenerate * 0.8:
+                    step = rng.uniform(-0.08, 0.08, size=2).astype(np.float32)
+                elif r < degenerate:
+                    step = (-last_step * np.float32(rng.uniform(0.5, 1.5))).astype(np.float32)
+                else:
+                    step = rng.uniform(-20, 20, size=2).astype(np.float32)
+                to = (cur + step).astype(np.float32)
+                k = int(rng.integers(0, 3))
+                if k == 0:
+                    b.line_to(tuple(to), attrs())
+                elif k == 1:
+                    far = rng.uniform() < 0.2
+                    ctrl = cur + rng.uniform(-30, 30, size=2).astype(np.float32) * np.float32(8.0 if far else 1.0)
+                    b.quadratic_bezier_to(tuple(ctrl.astype(np.float32)), tuple(to), attrs())
+                else:
+                    c1 = cur + rng.uniform(-30, 30, size=2).astype(np.float32)
+                    c2 = to + rng.uniform(-30, 30, size=2).astype(np.float32)
+                    b.cubic_bezier_to(tuple(c1.astype(np.float32)), tuple(c2.astype(np.float32)), tuple(to), attrs())
+                if np.any(step != 0):
+                    last_step = step
+                cur = to
+            b.end(bool(rng.uniform() < closed_fraction))
+        paths.append(b.build())
+    return PathBatch.from_paths(paths)
+
+
 def fixture_paths(golden_dir):
     return [parse_svg_path((golden_dir / "logo.path").read_text()), parse_svg_path((golden_dir / "rust_logo.path").read_text())]
 
