@@ -106,6 +106,15 @@ int lyon_cuda_flatten_quadratics_count(lyon_cuda_ctx* ctx, const float* d_ctrl, 
 int lyon_cuda_flatten_quadratics_emit(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance,
                                       const uint64_t* d_offsets, uint64_t total_points, float* d_points, float* d_t);
 
+/* Single pass: count, scan and emit in one kernel into buffers the caller keeps across calls (the steady-state form of
+ * the two calls above: `Vec`s that have reached their capacity).  d_offsets (n+1 u64) is written, d_points / d_t hold
+ * point_capacity points.  *total_points receives the exact total; when it exceeds point_capacity nothing is emitted
+ * and LYON_ERR_BUFFER_TOO_SMALL is returned (grow the buffers and call again). */
+int lyon_cuda_flatten_cubics_fused(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance, uint64_t* d_offsets,
+                                   float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points);
+int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance, uint64_t* d_offsets,
+                                       float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points);
+
 /* ---- stroke tessellation (lyon_tessellation::StrokeTessellator) ------------------------------------ */
 /* Equivalent of, for every path p of the batch in order,
  *     StrokeTessellator::new().tessellate_path(p, options, &mut BuffersBuilder::new(&mut out, ctor))

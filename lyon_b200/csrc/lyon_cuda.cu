@@ -52,13 +52,18 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
     return v;
 }
 // Called by all 32 lanes of ONE warp. Publishes `aggregate` for `tile`, returns the exclusive prefix.
-__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t tile, uint64_t aggregate) {
+// `published`: the caller already made the aggregate visible with lookback_publish (so that work which does not need
+// the prefix can run between the two).
+__device__ __forceinline__ void lookback_publish(uint64_t* desc, uint32_t tile, uint64_t aggregate) {
+    st_desc(&desc[tile], (tile == 0u ? ST_PREFIX : ST_AGG) | aggregate);
+}
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t tile, uint64_t aggregate, bool published = false) {
     const unsigned lane = threadIdx.x & 31u;
     if (tile == 0u) {
-        if (lane == 0u) st_desc(&desc[0], ST_PREFIX | aggregate);
+        if (lane == 0u && !published) st_desc(&desc[0], ST_PREFIX | aggregate);
         return 0ull;
     }
-    if (lane == 0u) st_desc(&desc[tile], ST_AGG | aggregate);
+    if (lane == 0u && !published) st_desc(&desc[tile], ST_AGG | aggregate);
     uint64_t excl = 0ull;
     int64_t look = (int64_t)tile - 1;
     for (;;) {
@@ -480,103 +485,160 @@ __global__ void __launch_bounds__(BLOCK) k_flat_count(const float* __restrict__ 
         totals->flat_points = s_base + local + cnt;
     }
 }
-// Emit pass of the standalone curve flattener.  A block owns FLAT_CURVES consecutive curves and walks their output
-// points in windows of FLAT_WINDOW:
-//   phase A  thread / curve   the SEQUENTIAL part only: t1 = t0 + step replayed in f32 (cubic_bezier.rs:605-611,
-//                             quadratic_bezier.rs:382-388); each t and its curve id go to shared memory.  The
-//                             polynomial coefficients (cubic_bezier.rs:1318-1325) are computed once per curve.
-//   phase B  thread / point   Horner evaluation (cubic_bezier.rs:1351-1365), the last point of a curve is the exact
-//                             endpoint; a warp stores 32 consecutive points = 256 contiguous bytes.
+// Emit pass of the standalone curve flattener.  A block owns FLAT_CURVES consecutive curves, one per thread, and moves
+// their output points through a shared-memory window:
+//   phase A  thread / curve   the thread keeps its curve's polynomial form (cubic_bezier.rs:1318-1325) in registers and
+//                             walks its points in order: t1 = t0 + step accumulated in f32 (cubic_bezier.rs:605-611,
+//                             quadratic_bezier.rs:382-388), Horner evaluation (cubic_bezier.rs:1351-1365), the last
+//                             point is the exact endpoint.  Points go to the window at their output position.
+//   phase B  thread / point   the window leaves the SM as contiguous 8-byte stores (a warp = 256 contiguous bytes).
 // HBM traffic: control points and offsets once, every output point once.
 constexpr int FLAT_CURVES = 256;
-constexpr int FLAT_WINDOW = 8192;
-constexpr uint16_t FLAT_LAST = 0x8000u;
+constexpr int FLAT_WINDOW = 8192;    // points per window (4096 when the curve parameters are written too)
 template <int NPTS>
 struct FlatSmem {
     unsigned long long off[FLAT_CURVES + 1];
-    float poly[FLAT_CURVES][2 * NPTS];  // a0..a(NPTS-1), then nothing: `to` lives in `to[]`
-    float to[FLAT_CURVES][2];
-    float t[FLAT_WINDOW];
-    uint16_t cid[FLAT_WINDOW];
+    float2 pts[FLAT_WINDOW];  // with t output: first half points, second half (as float) the parameters
 };
-template <int NPTS>
+// FUSED: one pass.  The block takes a ticket, counts its curves (Wang), gets the position of its first point by
+// decoupled look-back over the block totals, writes the offsets it was given to compute, and emits -- unless the
+// caller's point buffer is too small, in which case it only counts (lyon_cuda_flatten_*_fused then reports the size).
+struct FlatFused {
+    unsigned long long* offsets_out;  // [n + 1]
+    unsigned long long capacity;      // points the output buffers can hold
+    uint32_t* ticket;
+    uint64_t* desc;
+    Totals* totals;
+};
+template <int NPTS, bool FUSED>
 __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restrict__ ctrl, unsigned long long n, float tol,
                                                            const unsigned long long* __restrict__ offsets,
-                                                           float2* __restrict__ out, float* __restrict__ t_out) {
+                                                           float2* __restrict__ out, float* __restrict__ t_out, FlatFused fu) {
     extern __shared__ __align__(16) unsigned char flat_smem_raw[];
     FlatSmem<NPTS>& sm = *reinterpret_cast<FlatSmem<NPTS>*>(flat_smem_raw);
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_wsum[FLAT_CURVES / 32], s_base;
     const uint32_t tid = threadIdx.x;
-    const unsigned long long c0 = (unsigned long long)blockIdx.x * FLAT_CURVES;
+    uint32_t tile = blockIdx.x;
+    if (FUSED) {
+        if (tid == 0) s_tile = atomicAdd(fu.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    const unsigned long long c0 = (unsigned long long)tile * FLAT_CURVES;
     const uint32_t nc = (uint32_t)min((unsigned long long)FLAT_CURVES, n - c0);
-    for (uint32_t i = tid; i <= nc; i += FLAT_CURVES) sm.off[i] = offsets[c0 + i];
-    // stage the control points through the (not yet used) t window: coalesced 4-byte loads
-    float* stage = sm.t;
+    if (!FUSED)
+        for (uint32_t i = tid; i <= nc; i += FLAT_CURVES) sm.off[i] = offsets[c0 + i];
+    // stage the control points through the (not yet used) window: coalesced 4-byte loads
+    float* stage = reinterpret_cast<float*>(sm.pts);
     for (uint32_t i = tid; i < nc * 2u * NPTS; i += FLAT_CURVES) stage[i] = ctrl[c0 * 2ull * NPTS + i];
     __syncthreads();
-    float step = 0.0f, t = 0.0f;
-    uint32_t cnt = 0u, k = 0u;
+    float step = 0.0f;
+    uint32_t cnt = 0u;
+    V2 a0 = v2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0, to = a0;
     if (tid < nc) {
         const float* c = stage + tid * 2u * NPTS;
         float nseg;
         if (NPTS == 4) {
-            const V2 from = v2(c[0], c[1]), c1 = v2(c[2], c[3]), c2 = v2(c[4], c[5]), to = v2(c[6], c[7]);
+            const V2 from = v2(c[0], c[1]), c1 = v2(c[2], c[3]), c2 = v2(c[4], c[5]);
+            to = v2(c[6], c[7]);
             nseg = cubic_wang(from, c1, c2, to, tol);
             const CubicPoly q = cubic_poly(from, c1, c2, to);
-            float* d = sm.poly[tid];
-            d[0] = q.a0.x; d[1] = q.a0.y; d[2] = q.a1.x; d[3] = q.a1.y;
-            d[4] = q.a2.x; d[5] = q.a2.y; d[6] = q.a3.x; d[7] = q.a3.y;
-            sm.to[tid][0] = to.x;
-            sm.to[tid][1] = to.y;
+            a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3;
         } else {
-            const V2 from = v2(c[0], c[1]), cc = v2(c[2], c[3]), to = v2(c[4], c[5]);
+            const V2 from = v2(c[0], c[1]), cc = v2(c[2], c[3]);
+            to = v2(c[4], c[5]);
             nseg = quad_wang(from, cc, to, tol);
             const QuadPoly q = quad_poly(from, cc, to);
-            float* d = sm.poly[tid];
-            d[0] = q.a0.x; d[1] = q.a0.y; d[2] = q.a1.x; d[3] = q.a1.y; d[4] = q.a2.x; d[5] = q.a2.y;
-            sm.to[tid][0] = to.x;
-            sm.to[tid][1] = to.y;
+            a0 = q.a0; a1 = q.a1; a2 = q.a2;
         }
         step = 1.0f / nseg;
         cnt = to_u32_or_1(nseg);
     }
-    __syncthreads();  // `stage` (= sm.t) is free again
-    const unsigned long long base = sm.off[0];
-    const unsigned long long total = sm.off[nc] - base;
-    const unsigned long long my0 = tid < nc ? sm.off[tid] - base : 0ull;  // block-relative index of my first point
-    for (unsigned long long w0 = 0; w0 < total; w0 += FLAT_WINDOW) {
-        const unsigned long long w1 = min(total, w0 + (unsigned long long)FLAT_WINDOW);
+    unsigned long long base = 0ull, total = 0ull, my0 = 0ull;  // my0: block-relative index of my first point
+    if (FUSED) {
+        // exclusive scan of the counts inside the block (64-bit); the block total is published at once, the look-back
+        // for the block's base runs after the first window has been computed (phase A does not need it)
+        const unsigned lane = tid & 31u, wid = tid >> 5;
+        unsigned long long inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += y;
+        }
+        if (lane == 31u) s_wsum[wid] = inc;
+        __syncthreads();  // also: `stage` (= the window) is free again
+        unsigned long long wbase = 0ull;
+        for (int k = 0; k < FLAT_CURVES / 32; ++k) {
+            if (k < (int)wid) wbase += s_wsum[k];
+            total += s_wsum[k];
+        }
+        if (tid == 0) lookback_publish(fu.desc, tile, total);
+        my0 = wbase + inc - cnt;
+    } else {
+        __syncthreads();  // `stage` (= the window) is free again
+        base = sm.off[0];
+        total = sm.off[nc] - base;
+        my0 = tid < nc ? sm.off[tid] - base : 0ull;
+    }
+    const uint32_t window = t_out ? FLAT_WINDOW / 2 : FLAT_WINDOW;
+    float* const win_t = reinterpret_cast<float*>(sm.pts + FLAT_WINDOW / 2);
+    float2* gout = out + base;
+    float* gt = t_out ? t_out + base : nullptr;
+    bool resolved = !FUSED;
+    float t = 0.0f;
+    uint32_t k = 0u;
+    for (unsigned long long w0 = 0; w0 < total; w0 += window) {
+        const unsigned long long w1 = min(total, w0 + (unsigned long long)window);
         // ---- phase A
         while (k < cnt && my0 + k < w1) {
             const bool last = k + 1u == cnt;
-            if (!last) t = t + step;
+            V2 pos = to;
+            float tt = 1.0f;
+            if (!last) {
+                t = t + step;
+                tt = t;
+                float u = t;
+                pos = a0 + a1 * u;
+                u = u * t;
+                pos = pos + a2 * u;
+                if (NPTS == 4) {
+                    u = u * t;
+                    pos = pos + a3 * u;
+                }
+            }
             const uint32_t i = (uint32_t)(my0 + k - w0);
-            sm.t[i] = last ? 1.0f : t;
-            sm.cid[i] = (uint16_t)(tid | (last ? FLAT_LAST : 0u));
+            sm.pts[i] = make_float2(pos.x, pos.y);
+            if (t_out) win_t[i] = tt;
             ++k;
+        }
+        if (FUSED && !resolved) {
+            // the block's base: look-back by warp 0 (the first window is already computed), then offsets out
+            if (tid < 32) {
+                const uint64_t e = lookback_exclusive(fu.desc, tile, total, true);
+                if (tid == 0) s_base = e;
+            }
+            __syncthreads();
+            base = s_base;
+            resolved = true;
+            if (tid < nc) fu.offsets_out[c0 + tid] = base + my0;
+            if (tid == nc - 1u && c0 + nc == n) {
+                fu.offsets_out[n] = base + total;
+                fu.totals->flat_points = base + total;
+            }
+            if (base + total > fu.capacity) {
+                if (tid == 0) atomicOr(&fu.totals->error, 0x100u);  // point buffer too small: counted, not emitted
+                return;
+            }
+            gout = out + base;
+            gt = t_out ? t_out + base : nullptr;
         }
         __syncthreads();
         // ---- phase B
         const uint32_t wn = (uint32_t)(w1 - w0);
         for (uint32_t i = tid; i < wn; i += FLAT_CURVES) {
-            const uint16_t cw = sm.cid[i];
-            const uint32_t c = cw & 0xFFu;
-            const float tt = sm.t[i];
-            const float* d = sm.poly[c];
-            V2 pos;
-            if (cw & FLAT_LAST) {
-                pos = v2(sm.to[c][0], sm.to[c][1]);
-            } else if (NPTS == 4) {
-                CubicPoly q;
-                q.a0 = v2(d[0], d[1]); q.a1 = v2(d[2], d[3]); q.a2 = v2(d[4], d[5]); q.a3 = v2(d[6], d[7]);
-                pos = cubic_poly_sample(q, tt);
-            } else {
-                QuadPoly q;
-                q.a0 = v2(d[0], d[1]); q.a1 = v2(d[2], d[3]); q.a2 = v2(d[4], d[5]);
-                pos = quad_poly_sample(q, tt);
-            }
-            const unsigned long long s = base + w0 + i;
-            __stcs(out + s, make_float2(pos.x, pos.y));
-            if (t_out) __stcs(t_out + s, tt);
+            __stcs(gout + w0 + i, sm.pts[i]);
+            if (t_out) __stcs(gt + w0 + i, win_t[i]);
         }
         __syncthreads();
     }
@@ -802,12 +864,45 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
     if (!c || (n && (!d_ctrl || !d_offsets)) || (total && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
     if (n == 0 || total == 0) return LYON_OK;
     const size_t smem = sizeof(FlatSmem<NPTS>);
-    CU_TRY(c, cudaFuncSetAttribute(k_flat_emit<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_flat_emit<NPTS><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, (const unsigned long long*)d_offsets,
-                                                                                 (float2*)d_points, d_t);
+    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    k_flat_emit<NPTS, false><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(
+        d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return LYON_OK;
+}
+// One pass: count + look-back + emit into caller-kept buffers (see k_flat_emit<NPTS, true>).
+template <int NPTS>
+int flatten_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets, float* d_points,
+                  uint64_t capacity, float* d_t, uint64_t* total) {
+    if (!c || !total || (n && (!d_ctrl || !d_offsets)) || (capacity && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
+    if (!(tol > 0.0f)) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN / non-positive
+    *total = 0;
+    if (n == 0) {
+        if (d_offsets) CU_TRY(c, cudaMemsetAsync(d_offsets, 0, 8, c->stream));
+        return LYON_OK;
+    }
+    const unsigned tiles = grid_for(n, FLAT_CURVES);
+    TRY(ensure(c, c->misc, 512));
+    TRY(ensure(c, c->desc, (size_t)tiles * 8));
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 8, c->stream));
+    const size_t smem = sizeof(FlatSmem<NPTS>);
+    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    FlatFused fu{(unsigned long long*)d_offsets, capacity, d_ticket(c, 0), (uint64_t*)c->desc.p, d_totals(c)};
+    if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    k_flat_emit<NPTS, true><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+    if (c->timing) {
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    TRY(fetch_totals(c));
+    *total = c->h_totals->flat_points;
+    const bool too_small = (c->h_totals->error & 0x100u) != 0u;
+    CU_TRY(c, cudaMemsetAsync(&d_totals(c)->error, 0, 4, c->stream));  // the flag is not an emit/count mismatch
+    return too_small ? LYON_ERR_BUFFER_TOO_SMALL : LYON_OK;
 }
 
 
@@ -1153,6 +1248,15 @@ int lyon_cuda_flatten_quadratics_count(lyon_cuda_ctx* c, const float* d_ctrl, ui
 int lyon_cuda_flatten_quadratics_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol,
                                       const uint64_t* d_offsets, uint64_t total, float* d_points, float* d_t) {
     return flatten_emit<3>(c, d_ctrl, n, tol, d_offsets, total, d_points, d_t);
+}
+
+int lyon_cuda_flatten_cubics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
+                                   float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points) {
+    return flatten_fused<4>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
+}
+int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
+                                       float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points) {
+    return flatten_fused<3>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
 }
 
 int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t* n_vertices,

@@ -214,6 +214,34 @@ class DeviceTessellator:
             _raise(self.L, self.ctx, st)
         return (offsets, pts, t) if with_t else (offsets, pts)
 
+    def flatten_curves_fused(self, d_ctrl, npts: int, tolerance: float, with_t: bool = False):
+        """Single pass (count + scan + emit in one kernel) into buffers kept across calls; they grow when the batch
+        needs more room (one extra pass).  Returns views of the kept buffers, like flatten_curves."""
+        torch = self.torch
+        n = int(d_ctrl.shape[0])
+        fn = self.L.lyon_cuda_flatten_cubics_fused if npts == 4 else self.L.lyon_cuda_flatten_quadratics_fused
+        if getattr(self, "_fl_off", None) is None or self._fl_off.shape[0] < n + 1:
+            self._fl_off = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+        if getattr(self, "_fl_pts", None) is None:
+            self._fl_pts = torch.empty((0, 2), dtype=torch.float32, device=self.device)
+            self._fl_t = torch.empty((0,), dtype=torch.float32, device=self.device)
+        total = ctypes.c_uint64()
+        for _ in range(2):
+            if with_t and self._fl_t.shape[0] < self._fl_pts.shape[0]:
+                self._fl_t = torch.empty((self._fl_pts.shape[0],), dtype=torch.float32, device=self.device)
+            cap = int(self._fl_pts.shape[0])
+            st = fn(self.ctx, d_ctrl.data_ptr(), n, tolerance, self._fl_off.data_ptr(), self._fl_pts.data_ptr() if cap else None,
+                    cap, self._fl_t.data_ptr() if (with_t and cap) else None, ctypes.byref(total))
+            if st != _ffi.ERR_BUFFER_TOO_SMALL:
+                break
+            self._fl_pts = None
+            self._fl_pts = torch.empty((int(total.value * 1.02) + 16, 2), dtype=torch.float32, device=self.device)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        nt = int(total.value)
+        out = (self._fl_off[: n + 1], self._fl_pts[:nt])
+        return out + (self._fl_t[:nt],) if with_t else out
+
     def launch_count(self) -> int:
         return int(self.L.lyon_cuda_launch_count(self.ctx))
 

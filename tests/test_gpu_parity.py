@@ -220,6 +220,24 @@ def test_host_buffer_entry_point(tz):
 
 
 @pytest.mark.parametrize("npts", [3, 4])
+def test_flatten_curves_fused(tz, npts, route):
+    """Single-pass flattening (count + look-back + emit in one kernel, buffers kept across calls): same bytes as the
+    oracle, including after the kept buffers had to grow and when they are larger than needed."""
+    if route != "tile":
+        pytest.skip("flattening has a single route")
+    import torch
+    rng = np.random.default_rng(5)
+    for n in (70000, 1000, 257, 1, 0):
+        ctrl = rng.uniform(-300, 300, size=(n, 2 * npts)).astype(np.float32)
+        d = torch.from_numpy(ctrl).cuda().reshape(n, 2 * npts)
+        off, pts, t = tz.flatten_curves_fused(d, npts, 0.02, with_t=True)
+        torch.cuda.synchronize()
+        ooff, opts, ot = (O.flatten_cubics if npts == 4 else O.flatten_quadratics)(ctrl, 0.02, with_t=True)
+        assert np.array_equal(off.cpu().numpy().astype(np.uint64), ooff)
+        assert pts.cpu().numpy().tobytes() == opts.tobytes() and t.cpu().numpy().tobytes() == ot.tobytes()
+
+
+@pytest.mark.parametrize("npts", [3, 4])
 def test_flatten_curves(tz, npts, route):
     if route != "tile":
         pytest.skip("flattening has a single route")
