@@ -6,9 +6,10 @@
 
 Workload (BASELINE.json configs[2], "C3"): 1M synthetic paths x 64 mixed line/quad/cubic segments, stroke width 2,
 round joins + round caps, tolerance 0.1.  STRONG scaling: the 1M-path batch is partitioned across the N GPUs by
-cumulative segment count; the only collective is an all-gather of per-rank vertex/index totals between the count and
-the emit pass (global index rebasing).  A "step" = count passes + scans + emit pass over the rank's whole slice, inputs
-already resident in HBM.  `value` = output vertices of all ranks / max-over-ranks device time.
+cumulative segment count; the only collective is an all-gather of per-rank vertex/index totals (global index
+rebasing: every rank emits with local ids in one pass, then adds its base to its indices).  A "step" = pre-pass +
+fused count/scan/emit kernel (+ all-gather + index rebase at N>1) over the rank's whole slice, inputs already resident in
+HBM.  `value` = output vertices of all ranks / max-over-ranks device time.
 
 Also reported on the same JSON line:
   e2e           the same metric through the host-buffer API (pinned host inputs, H2D, kernels, D2H of all output)
@@ -225,8 +226,9 @@ def main():
     kernel_ms = []
 
     def step(ev=None, record=False):
-        """N=1: ONE pass -- lyon_cuda_stroke_fused (pre-pass, then count+scan+emit fused in the tile kernel) into
-        buffers kept across steps.  N>1: plan (count), all-gather of {V_r, I_r} for global index rebasing, emit."""
+        """ONE pass -- lyon_cuda_stroke_fused (pre-pass, then count+scan+emit fused in the tile kernel) into buffers kept
+        across steps.  N>1: the rank's slice is emitted with local ids, then the all-gather of {V_r, I_r} and a streaming
+        rebase of the rank's indices (lyon_cuda_rebase_indices) make the ids global."""
         nonlocal verts, idx
         if ev:
             ev[0].record()
@@ -234,12 +236,10 @@ def main():
             v, i = tz.stroke_fused(dbatch, opts)
             nv, ni = int(v.shape[0]), int(i.shape[0])
         else:
-            nv, ni = tz.stroke_plan(dbatch, opts)
+            v, i = tz.stroke_fused(dbatch, opts)  # local ids
+            nv, ni = int(v.shape[0]), int(i.shape[0])
             base, _ibase, _tot = exchange_totals(nv, ni, device=dev)  # the one collective: 16 B per rank over NCCL
-            if verts is None or verts.shape[0] < nv or idx.shape[0] < ni:
-                verts = torch.empty((nv, 8), dtype=torch.float32, device=dev)
-                idx = torch.empty((ni,), dtype=torch.int32, device=dev)
-            tz.stroke_emit(nv, ni, vertex_base=base, vertices=verts, indices=idx)
+            tz.rebase_indices(i, nv, base)  # global ids: one streaming pass over this rank's indices
         if ev:
             ev[1].record()
         if record:
@@ -280,7 +280,7 @@ def main():
     k_ms = sum(kernel_ms) / len(kernel_ms)
     k_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_stroke_tile<FUSED>" if world == 1 else "k_stroke_tile<EMIT>", "achieved": k_gbs,
+        "bound": "hbm", "kernel": "k_stroke_tile<FUSED>", "achieved": k_gbs,
         "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms": dev_ms / args.steps,
         "kernel_share_of_step": k_ms / (dev_ms / args.steps),

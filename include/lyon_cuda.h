@@ -145,6 +145,14 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, c
                            uint64_t index_capacity, uint64_t vertex_base, uint64_t* d_path_vertex_end,
                            uint64_t* d_path_index_end, uint64_t* n_vertices, uint64_t* n_indices);
 
+/* Adds vertex_base to every index of a mesh that was emitted with vertex_base 0: BuffersBuilder::with_vertex_offset
+ * (geometry_builder.rs:325-329) applied after the fact.  Multi-GPU use: every rank runs the single-pass
+ * lyon_cuda_stroke_fused on its slice, the ranks all-gather {V_r, I_r}, and rank r rebases by sum(V_q, q < r) -- one
+ * streaming pass over the indices instead of a separate count pass before the emit.  n_vertices is the number of
+ * vertices of the mesh (TooManyVertices when vertex_base + n_vertices - 1 would pass u32::MAX - 1). */
+int lyon_cuda_rebase_indices(lyon_cuda_ctx* ctx, uint32_t* d_indices, uint64_t n_indices, uint64_t n_vertices,
+                             uint64_t vertex_base);
+
 /* Pipeline selection for plan/emit/fused: 0 = automatic (shared-memory tile pipeline whenever every path of the
  * batch fits a tile), 1 = always the general multi-kernel pipeline (any path length).  Results are identical. */
 int lyon_cuda_set_pipeline(lyon_cuda_ctx* ctx, int pipeline);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "lyon_cuda_flatten_cubics_count", "lyon_cuda_flatten_cubics_emit",
     "lyon_cuda_flatten_quadratics_count", "lyon_cuda_flatten_quadratics_emit",
     "lyon_cuda_flatten_cubics_fused", "lyon_cuda_flatten_quadratics_fused",
-    "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check", "lyon_cuda_stroke_fused", "lyon_cuda_set_pipeline",
+    "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check", "lyon_cuda_stroke_fused", "lyon_cuda_rebase_indices", "lyon_cuda_set_pipeline",
     "lyon_cuda_enable_timing", "lyon_cuda_last_kernel_ms",
     "lyon_cuda_tessellate_paths", "lyon_cuda_free_host",
 ]
@@ -86,6 +86,7 @@ def lib():
     L.lyon_cuda_check.argtypes = [vp]
     L.lyon_cuda_stroke_fused.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), vp, u64, vp, u64, u64,
                                          vp, vp, pu64, pu64]
+    L.lyon_cuda_rebase_indices.argtypes = [vp, vp, u64, u64, u64]
     L.lyon_cuda_set_pipeline.argtypes = [vp, ctypes.c_int]
     L.lyon_cuda_enable_timing.argtypes = [vp, ctypes.c_int]
     L.lyon_cuda_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]

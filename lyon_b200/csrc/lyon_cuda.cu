@@ -644,6 +644,27 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
     }
 }
 
+// Global index rebasing of a mesh emitted with vertex_base 0 (multi-GPU: a rank learns the number of vertices emitted
+// by the ranks before it only after its own single-pass emit): indices[i] += base, 16 bytes per thread and iteration.
+__global__ void __launch_bounds__(256) k_rebase_indices(uint32_t* __restrict__ idx, unsigned long long n, uint32_t base) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long head = min(n, (unsigned long long)((16u - ((uintptr_t)idx & 15u)) & 15u) / 4ull);  // to 16-byte alignment
+    if (i < head) idx[i] += base;
+    uint4* v = reinterpret_cast<uint4*>(idx + head);
+    const unsigned long long nv = (n - head) / 4ull;
+    for (unsigned long long k = i; k < nv; k += stride) {
+        uint4 q = v[k];
+        q.x += base;
+        q.y += base;
+        q.z += base;
+        q.w += base;
+        v[k] = q;
+    }
+    const unsigned long long tail0 = head + nv * 4ull;
+    if (tail0 + i < n && i < 4ull) idx[tail0 + i] += base;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Variable line width (stroke_vw.cuh): one thread per path runs the streaming state machine, once to count, once to emit.
 // ---------------------------------------------------------------------------------------------------------
@@ -1450,6 +1471,20 @@ int lyon_cuda_last_kernel_ms(lyon_cuda_ctx* c, float* ms) {
     if (!c->ev_valid) return LYON_ERR_INVALID_ARGUMENT;
     CU_TRY(c, cudaEventSynchronize(c->ev1));
     CU_TRY(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return LYON_OK;
+}
+
+int lyon_cuda_rebase_indices(lyon_cuda_ctx* c, uint32_t* d_indices, uint64_t n_indices, uint64_t n_vertices, uint64_t vertex_base) {
+    if (!c || (n_indices && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+    // ids handed out become vertex_base .. vertex_base + V - 1 and must stay <= u32::MAX - 1 (geometry_builder.rs:342-346)
+    if (n_vertices && vertex_base + n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (n_indices == 0 || vertex_base == 0) return LYON_OK;
+    unsigned blocks = grid_for((n_indices + 3) / 4, 256);
+    const unsigned cap = (unsigned)c->num_sms * 32u;
+    if (blocks > cap) blocks = cap;
+    k_rebase_indices<<<blocks, 256, 0, c->stream>>>(d_indices, n_indices, (uint32_t)vertex_base);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
     return LYON_OK;
 }
 

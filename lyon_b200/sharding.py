@@ -4,8 +4,8 @@ Paths are independent units of work -- the reference creates a fresh ``StrokeBui
 (``crates/tessellation/src/stroke.rs:133-134``) and only the sub-paths of ONE path share state (the advancement carry,
 ``stroke.rs:1359``) -- so a batch is cut into ``world`` contiguous path ranges of equal cumulative segment count and
 every rank tessellates its own range.  The single exchange on the path is an all-gather of the per-rank output totals
-``{V_r, I_r}`` (16 bytes per rank; NCCL over NVLink on the GPUs, gloo in the CPU tests): rank ``r`` emits its indices
-rebased by ``sum(V_q for q < r)`` -- what ``BuffersBuilder::with_vertex_offset`` does in the reference
+``{V_r, I_r}`` (16 bytes per rank; NCCL over NVLink on the GPUs, gloo in the CPU tests): rank ``r`` emits (or, after a single-pass emit, rebases) its indices
+by ``sum(V_q for q < r)`` -- what ``BuffersBuilder::with_vertex_offset`` does in the reference
 (``crates/tessellation/src/geometry_builder.rs:325-329``) -- so that the concatenation of the per-rank buffers is
 bit-for-bit the single-GPU result.  Outputs stay resident per GPU.
 """
@@ -74,3 +74,12 @@ class ShardedStroker:
         self.vertex_base, self.index_base, self.totals = exchange_totals(nv, ni, self.group, self.device)
         check_global_vertex_count(self.totals)
         return self.tz.stroke_emit(nv, ni, vertex_base=self.vertex_base, vertices=vertices, indices=indices)
+
+    def run_single_pass(self, dbatch, options, vertices=None, indices=None):
+        """Same result with ONE pass over the slice: the fused count+scan+emit kernel with local ids, the all-gather of
+        ``{V_r, I_r}``, then a streaming rebase of this rank's indices (``lyon_cuda_rebase_indices``)."""
+        v, i = self.tz.stroke_fused(dbatch, options, vertices=vertices, indices=indices)
+        self.vertex_base, self.index_base, self.totals = exchange_totals(int(v.shape[0]), int(i.shape[0]), self.group, self.device)
+        check_global_vertex_count(self.totals)
+        self.tz.rebase_indices(i, int(v.shape[0]), self.vertex_base)
+        return v, i

@@ -166,6 +166,13 @@ class DeviceTessellator:
         out = (vertices[:nv.value], indices[:ni.value])
         return out + (pve, pie) if with_ranges else out
 
+    def rebase_indices(self, indices, n_vertices: int, vertex_base: int):
+        """indices += vertex_base in place (lyon_cuda_rebase_indices): global index rebasing after a single-pass emit."""
+        st = self.L.lyon_cuda_rebase_indices(self.ctx, indices.data_ptr(), int(indices.shape[0]), int(n_vertices), int(vertex_base))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return indices
+
     def set_pipeline(self, general: bool):
         """False: automatic (fused shared-memory tile pipeline when every path fits a tile); True: always the
         general multi-kernel pipeline.  Both produce identical output."""

@@ -209,6 +209,36 @@ def test_vertex_base_and_too_many_vertices(tz):
         gpu_stroke(tz, batch, o, vertex_base=0xFFFFFFFE)
 
 
+def test_rebase_indices(tz, route):
+    """lyon_cuda_rebase_indices: a mesh emitted with local ids, rebased afterwards == emitted with the base (the
+    multi-GPU single-pass flow), for every alignment of the index buffer."""
+    if route != "tile":
+        pytest.skip("one route")
+    import torch
+    from lyon_b200 import TooManyVertices
+    batch = W.c3_mixed_paths(500, 16, seed=3)
+    o = StrokeOptions(line_join=LineJoin.Round)
+    d = tz.upload(batch)
+    v0, i0 = tz.stroke_fused(d, o)
+    i0 = i0.clone()
+    v1, i1 = tz.stroke_fused(d, o, vertex_base=54321)
+    want = i1.clone()
+    for shift in range(4):  # index views starting at every 4-byte offset inside a 16-byte line
+        buf = torch.zeros(i0.shape[0] + 8, dtype=torch.int32, device=i0.device)
+        view = buf[shift:shift + i0.shape[0]]
+        view.copy_(i0)
+        tz.rebase_indices(view, int(v0.shape[0]), 54321)
+        torch.cuda.synchronize()
+        assert torch.equal(view, want) and int(buf[:shift].abs().sum()) == 0 and int(buf[shift + i0.shape[0]:].abs().sum()) == 0
+    for n in (0, 1, 2, 3, 5):
+        small = i0[:n].clone()
+        tz.rebase_indices(small, int(v0.shape[0]), 7)
+        torch.cuda.synchronize()
+        assert torch.equal(small, i0[:n] + 7)
+    with pytest.raises(TooManyVertices):
+        tz.rebase_indices(i0.clone(), int(v0.shape[0]), 0xFFFFFFFE)
+
+
 def test_host_buffer_entry_point(tz):
     from lyon_b200 import StrokeTessellator, tessellate_paths
     batch = W.random_small_paths(200, 77)
