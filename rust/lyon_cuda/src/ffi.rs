@@ -82,6 +82,14 @@ extern "C" {
                                   vertex_capacity: u64, d_indices: *mut u32, index_capacity: u64, vertex_base: u64,
                                   d_path_vertex_end: *mut u64, d_path_index_end: *mut u64, n_vertices: *mut u64,
                                   n_indices: *mut u64) -> c_int;
+    pub fn lyon_cuda_flatten_cubics_fused(ctx: *mut lyon_cuda_ctx, d_ctrl: *const f32, n: u64, tolerance: f32,
+                                          d_offsets: *mut u64, d_points: *mut f32, point_capacity: u64, d_t: *mut f32,
+                                          total_points: *mut u64) -> c_int;
+    pub fn lyon_cuda_flatten_quadratics_fused(ctx: *mut lyon_cuda_ctx, d_ctrl: *const f32, n: u64, tolerance: f32,
+                                              d_offsets: *mut u64, d_points: *mut f32, point_capacity: u64, d_t: *mut f32,
+                                              total_points: *mut u64) -> c_int;
+    pub fn lyon_cuda_rebase_indices(ctx: *mut lyon_cuda_ctx, d_indices: *mut u32, n_indices: u64, n_vertices: u64,
+                                    vertex_base: u64) -> c_int;
     pub fn lyon_cuda_set_pipeline(ctx: *mut lyon_cuda_ctx, pipeline: c_int) -> c_int;
     pub fn lyon_cuda_enable_timing(ctx: *mut lyon_cuda_ctx, on: c_int) -> c_int;
     pub fn lyon_cuda_last_kernel_ms(ctx: *mut lyon_cuda_ctx, ms: *mut f32) -> c_int;

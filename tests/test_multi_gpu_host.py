@@ -52,6 +52,9 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         vbase, ibase, totals = exchange_totals(len(sizes.vertices), len(sizes.indices))
         assert totals.shape == (world, 2)
         got = E.stroke_batch(mine, _opts(), vertex_base=vbase, pipeline="tile")
+        # the single-pass flow of bench.py at N>1: local ids, then the rank's indices rebased by its vertex base
+        assert np.array_equal(sizes.indices + np.uint32(vbase), got.indices)
+        assert sizes.vertices.tobytes() == got.vertices.tobytes()
         np.save(os.path.join(out_dir, f"v{rank}.npy"), got.vertices)
         np.save(os.path.join(out_dir, f"i{rank}.npy"), got.indices)
         np.save(os.path.join(out_dir, f"b{rank}.npy"), np.array([vbase, ibase, cuts[rank], cuts[rank + 1]]))
