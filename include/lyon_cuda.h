@@ -115,6 +115,16 @@ int lyon_cuda_flatten_cubics_fused(lyon_cuda_ctx* ctx, const float* d_ctrl, uint
 int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* ctx, const float* d_ctrl, uint64_t n, float tolerance, uint64_t* d_offsets,
                                        float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points);
 
+/* Path-level flattening: the `Flattened` adapter, `path.iter().flattened(tolerance)` (crates/path/src/iterator.rs:125-226,
+ * PathEvent::Quadratic / Cubic -> the Line events of `segment.flattened(tolerance)`), for every path of a batch.  The
+ * output is a batch in the same encoding (verbs Begin / LineTo / Close / End only; Close stores the first point again)
+ * and can be fed back to any entry point.  Paths without custom attributes.  Pass 1 returns the sizes; pass 2 writes
+ * d_out_verbs[n_out_verbs], d_out_points[2 * n_out_points] and the two n_paths + 1 range arrays. */
+int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, float tolerance, uint64_t* n_out_verbs,
+                                  uint64_t* n_out_points);
+int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* ctx, uint8_t* d_out_verbs, float* d_out_points, uint32_t* d_out_path_verb_begin,
+                                 uint32_t* d_out_path_point_begin);
+
 /* ---- stroke tessellation (lyon_tessellation::StrokeTessellator) ------------------------------------ */
 /* Equivalent of, for every path p of the batch in order,
  *     StrokeTessellator::new().tessellate_path(p, options, &mut BuffersBuilder::new(&mut out, ctor))

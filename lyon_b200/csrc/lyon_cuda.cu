@@ -644,6 +644,146 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Path-level flattening: the `Flattened` adapter (crates/path/src/iterator.rs:125-226) over a whole batch.  Every
+// QuadraticTo / CubicTo becomes the LineTo sequence of its flattened points (for_each_flattened: plain Wang counts, no
+// sharp-turn split -- that one belongs to the stroker); Begin / LineTo / Close / End pass through.  Paths without
+// custom attributes.  One warp per path in both passes; a lane owns a verb and writes its points in order.
+// ---------------------------------------------------------------------------------------------------------
+struct PfRec {  // per input verb, written by the count pass
+    float n;          // Wang count of a curve (f32, possibly non-integer), 1 otherwise
+    uint32_t voff;    // first output verb, relative to the path's first output verb
+    uint32_t poff;    // first output point, relative to the path's first output point
+    uint32_t pt;      // first stored input point of the verb
+};
+__device__ __forceinline__ uint32_t pf_count(uint8_t verb, const V2* points, uint32_t pt, float tol, float* n_out) {
+    float n = 1.0f;
+    if (verb == VERB_CUBIC) n = cubic_wang(seg_from_point(points, pt, 0u), points[pt], points[pt + 1], points[pt + 2], tol);
+    else if (verb == VERB_QUAD) n = quad_wang(seg_from_point(points, pt, 0u), points[pt], points[pt + 1], tol);
+    *n_out = n;
+    return (verb == VERB_CUBIC || verb == VERB_QUAD) ? to_u32_or_1(n) : 1u;
+}
+__global__ void __launch_bounds__(256) k_pf_count(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+                                                  const uint32_t* __restrict__ path_verb_begin,
+                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, float tol,
+                                                  PfRec* __restrict__ rec, uint32_t* __restrict__ path_nv,
+                                                  uint32_t* __restrict__ path_np, Totals* totals) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t path = warp; path < n_paths; path += nwarps) {
+        const uint32_t vb = path_verb_begin[path], ve = path_verb_begin[path + 1];
+        uint32_t pt_run = path_point_begin[path];
+        unsigned long long v_run = 0ull, p_run = 0ull;
+        for (uint32_t v0 = vb; v0 < ve; v0 += 32u) {
+            const uint32_t v = v0 + lane;
+            const bool valid = v < ve;
+            const uint8_t verb = valid ? verbs[v] : (uint8_t)VERB_END;
+            const uint32_t npts = valid ? verb_point_count(verb, 0u) : 0u;
+            uint32_t inc = npts;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (unsigned)o) inc += y;
+            }
+            const uint32_t pt = pt_run + inc - npts;
+            float n = 1.0f;
+            const uint32_t cnt = valid ? pf_count(verb, points, pt, tol, &n) : 0u;
+            const uint32_t pcnt = (valid && verb == VERB_END) ? 0u : cnt;  // End carries no point
+            unsigned long long iv = cnt, ip = pcnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, iv, o), z = __shfl_up_sync(0xffffffffu, ip, o);
+                if (lane >= (unsigned)o) {
+                    iv += y;
+                    ip += z;
+                }
+            }
+            if (valid) {
+                *reinterpret_cast<uint4*>(rec + v) =
+                    make_uint4(__float_as_uint(n), (uint32_t)(v_run + iv - cnt), (uint32_t)(p_run + ip - pcnt), pt);
+            }
+            pt_run += __shfl_sync(0xffffffffu, inc, 31);
+            v_run += __shfl_sync(0xffffffffu, iv, 31);
+            p_run += __shfl_sync(0xffffffffu, ip, 31);
+        }
+        if (lane == 0u) {
+            if (v_run > 0xFFFFFFFFull || p_run > 0xFFFFFFFFull) atomicOr(&totals->error, 2u);
+            path_nv[path] = (uint32_t)v_run;
+            path_np[path] = (uint32_t)p_run;
+            if (pt_run != path_point_begin[path + 1]) atomicOr(&totals->error, 4u);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+                                                 const uint32_t* __restrict__ path_verb_begin,
+                                                 const uint32_t* __restrict__ path_point_begin, uint32_t n_paths,
+                                                 const PfRec* __restrict__ rec, const unsigned long long* __restrict__ out_v0,
+                                                 const unsigned long long* __restrict__ out_p0, uint8_t* __restrict__ out_verbs,
+                                                 V2* __restrict__ out_points, uint32_t* __restrict__ out_path_verb_begin,
+                                                 uint32_t* __restrict__ out_path_point_begin) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t path = warp; path < n_paths; path += nwarps) {
+        const uint32_t vb = path_verb_begin[path], ve = path_verb_begin[path + 1];
+        const unsigned long long v0 = out_v0[path], p0 = out_p0[path];
+        if (lane == 0u) {
+            out_path_verb_begin[path] = (uint32_t)v0;
+            out_path_point_begin[path] = (uint32_t)p0;
+            if (path + 1u == n_paths) {
+                out_path_verb_begin[n_paths] = (uint32_t)out_v0[n_paths];
+                out_path_point_begin[n_paths] = (uint32_t)out_p0[n_paths];
+            }
+        }
+        const V2 first_of_path = points[path_point_begin[path]];
+        (void)first_of_path;
+        for (uint32_t v = vb + lane; v < ve; v += 32u) {
+            const uint8_t verb = verbs[v];
+            const uint4 q = *reinterpret_cast<const uint4*>(rec + v);
+            const float n = __uint_as_float(q.x);
+            uint8_t* ov = out_verbs + v0 + q.y;
+            V2* op = out_points + p0 + q.z;
+            const uint32_t pt = q.w;
+            if (verb == VERB_CUBIC || verb == VERB_QUAD) {
+                const bool cubic = verb == VERB_CUBIC;
+                const V2 from = seg_from_point(points, pt, 0u);
+                const V2 to = points[pt + (cubic ? 2u : 1u)];
+                V2 a1, a2, a3 = v2(0.0f, 0.0f);
+                if (cubic) {
+                    const CubicPoly c = cubic_poly(from, points[pt], points[pt + 1], to);
+                    a1 = c.a1; a2 = c.a2; a3 = c.a3;
+                } else {
+                    const QuadPoly c = quad_poly(from, points[pt], to);
+                    a1 = c.a1; a2 = c.a2;
+                }
+                const uint32_t cnt = to_u32_or_1(n);
+                const float step = 1.0f / n;
+                float t = 0.0f;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    V2 pos = to;
+                    if (k + 1u < cnt) {
+                        t = t + step;
+                        float u = t;
+                        pos = from + a1 * u;
+                        u = u * t;
+                        pos = pos + a2 * u;
+                        if (cubic) {
+                            u = u * t;
+                            pos = pos + a3 * u;
+                        }
+                    }
+                    ov[k] = VERB_LINE;
+                    op[k] = pos;
+                }
+            } else {
+                ov[0] = verb;
+                if (verb != VERB_END) op[0] = points[pt];  // Begin / LineTo / Close (the first point stored again)
+            }
+        }
+    }
+}
+
 // Global index rebasing of a mesh emitted with vertex_base 0 (multi-GPU: a rank learns the number of vertices emitted
 // by the ranks before it only after its own single-pass emit): indices[i] += base, 16 bytes per thread and iteration.
 __global__ void __launch_bounds__(256) k_rebase_indices(uint32_t* __restrict__ idx, unsigned long long n, uint32_t base) {
@@ -775,6 +915,9 @@ struct lyon_cuda_ctx {
     bool tile_planned = false;            // the last plan went through the tile pipeline
     bool vw_planned = false;              // the last plan went through the variable-width (thread per path) kernels
     DevBuf vw_nv, vw_nt, vw_v0, vw_t0;
+    DevBuf pf_rec;  // path-level flattening: per-verb records (counts reuse vw_nv / vw_nt / vw_v0 / vw_t0)
+    bool pf_planned = false;
+    lyon_path_batch pf_batch{};
     lyon_path_batch vw_batch{};
     lyon_path_batch tile_batch{};
     uint32_t tile_n_tiles = 0, tile_s_cap = 0, tile_w_v = 0, tile_w_t = 0, tile_quantum = 0;
@@ -1229,7 +1372,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
-                      &c->vw_nv, &c->vw_nt, &c->vw_v0, &c->vw_t0, &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
+                      &c->pf_rec, &c->vw_nv, &c->vw_nt, &c->vw_v0, &c->vw_t0, &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -1278,6 +1421,88 @@ int lyon_cuda_flatten_cubics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64
 int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
                                        float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points) {
     return flatten_fused<3>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
+}
+
+int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, uint64_t* n_out_verbs,
+                                  uint64_t* n_out_points) {
+    if (!c || !b || !n_out_verbs || !n_out_points) return LYON_ERR_INVALID_ARGUMENT;
+    *n_out_verbs = *n_out_points = 0;
+    c->pf_planned = false;
+    if (!(tol > 0.0f)) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN / non-positive
+    if (b->num_attributes != 0) {
+        c->err = "lyon_cuda_flatten_paths: paths with custom attributes are not supported";
+        return LYON_ERR_UNSUPPORTED_PARAMETER;
+    }
+    c->pf_batch = *b;
+    if (b->n_paths == 0 || b->n_verbs == 0) {
+        c->pf_planned = true;
+        return LYON_OK;
+    }
+    if (!b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
+    const uint32_t np = b->n_paths;
+    TRY(ensure(c, c->pf_rec, ((size_t)b->n_verbs + 1) * sizeof(PfRec)));
+    TRY(ensure(c, c->vw_nv, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->vw_nt, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->vw_v0, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->vw_t0, ((size_t)np + 1) * 8));
+    TRY(ensure(c, c->misc, 512));
+    const unsigned tiles = grid_for(np, BLOCK * 4);
+    TRY(ensure(c, c->desc, (size_t)tiles * 16));
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 16, c->stream));
+    unsigned blocks = (np + 7u) / 8u;
+    if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
+    k_pf_count<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
+                                             b->path_point_begin, np, tol, (PfRec*)c->pf_rec.p, (uint32_t*)c->vw_nv.p,
+                                             (uint32_t*)c->vw_nt.p, d_totals(c));
+    k_scan_counts<<<tiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, np, (unsigned long long*)c->vw_v0.p, d_ticket(c, 0),
+                                                 (uint64_t*)c->desc.p);
+    k_scan_counts<<<tiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nt.p, np, (unsigned long long*)c->vw_t0.p, d_ticket(c, 1),
+                                                 (uint64_t*)c->desc.p + tiles);
+    c->launches += 3;
+    CU_TRY(c, cudaGetLastError());
+    unsigned long long tot[2] = {0ull, 0ull};
+    CU_TRY(c, cudaMemcpyAsync(&tot[0], (unsigned long long*)c->vw_v0.p + np, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&tot[1], (unsigned long long*)c->vw_t0.p + np, 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(fetch_totals(c));
+    const unsigned err = c->h_totals->error;
+    CU_TRY(c, cudaMemsetAsync(&d_totals(c)->error, 0, 4, c->stream));
+    if (err & 4u) {
+        c->err = "path_point_begin does not match the points the verbs consume";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    if ((err & 2u) || tot[0] > 0xFFFFFFFFull || tot[1] > 0xFFFFFFFFull) {
+        c->err = "flattened batch does not fit 32-bit verb / point ranges";
+        return LYON_ERR_TOO_MANY_VERTICES;
+    }
+    *n_out_verbs = tot[0];
+    *n_out_points = tot[1];
+    c->pf_planned = true;
+    return LYON_OK;
+}
+int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* c, uint8_t* d_out_verbs, float* d_out_points, uint32_t* d_out_path_verb_begin,
+                                 uint32_t* d_out_path_point_begin) {
+    if (!c || !d_out_path_verb_begin || !d_out_path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
+    if (!c->pf_planned) {
+        c->err = "lyon_cuda_flatten_paths_emit without a successful lyon_cuda_flatten_paths_count";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    const lyon_path_batch& b = c->pf_batch;
+    if (b.n_paths == 0 || b.n_verbs == 0) {
+        CU_TRY(c, cudaMemsetAsync(d_out_path_verb_begin, 0, 4ull * ((size_t)b.n_paths + 1), c->stream));
+        CU_TRY(c, cudaMemsetAsync(d_out_path_point_begin, 0, 4ull * ((size_t)b.n_paths + 1), c->stream));
+        return LYON_OK;
+    }
+    if (!d_out_verbs || !d_out_points) return LYON_ERR_INVALID_ARGUMENT;
+    unsigned blocks = (b.n_paths + 7u) / 8u;
+    if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
+    k_pf_emit<<<blocks, 256, 0, c->stream>>>(b.verbs, reinterpret_cast<const V2*>(b.points), b.path_verb_begin, b.path_point_begin,
+                                            b.n_paths, (const PfRec*)c->pf_rec.p, (const unsigned long long*)c->vw_v0.p,
+                                            (const unsigned long long*)c->vw_t0.p, d_out_verbs, reinterpret_cast<V2*>(d_out_points),
+                                            d_out_path_verb_begin, d_out_path_point_begin);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
 }
 
 int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t* n_vertices,

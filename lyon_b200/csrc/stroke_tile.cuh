@@ -196,7 +196,32 @@ LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t s
     uint32_t s = sa;
     while (s < sb) {
 #ifdef __CUDA_ARCH__
-        // A run of ordinary points: the bare f32 addition chain, four slots (one 16-byte load / store) at a time.  The
+        // 32 ordinary points: eight 16-byte loads first, then the 32 dependent additions, then eight 16-byte stores --
+        // two instructions per point, nothing but the additions on the critical path.
+        if ((s & 3u) == 0u && s + 32u <= sb && m >= 1u && last_kept == s - 1u) {
+            const uint32_t sh = s & 31u;
+            uint32_t bits = special[s >> 5] >> sh;
+            if (sh) bits |= special[(s >> 5) + 1u] << (32u - sh);
+            if (bits == 0u) {
+                float4 l[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(len + s + 4 * q);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    l[q].x = adv = adv + l[q].x;
+                    l[q].y = adv = adv + l[q].y;
+                    l[q].z = adv = adv + l[q].z;
+                    l[q].w = adv = adv + l[q].w;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(w.adv + s + 4 * q) = l[q];
+                m += 32u;
+                last_kept = s + 31u;
+                s += 32u;
+                continue;
+            }
+        }
+        // A shorter run of ordinary points: the bare f32 addition chain, four slots (one 16-byte load / store) at a time.  The
         // next quad's lengths are loaded before this quad's results are stored (the arrays may alias as far as the
         // compiler knows), so the loads stay off the dependent chain.
         if ((s & 3u) == 0u && s + 4u <= sb && m >= 1u && last_kept == s - 1u) {

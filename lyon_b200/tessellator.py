@@ -221,6 +221,28 @@ class DeviceTessellator:
             _raise(self.L, self.ctx, st)
         return (offsets, pts, t) if with_t else (offsets, pts)
 
+    def flatten_paths(self, dbatch: DeviceBatch, tolerance: float) -> DeviceBatch:
+        """`path.iter().flattened(tolerance)` for every path of the batch (lyon_cuda_flatten_paths_*): a device batch
+        of polylines in the same encoding."""
+        torch = self.torch
+        nv, npt = ctypes.c_uint64(), ctypes.c_uint64()
+        cb = dbatch.c_struct()
+        st = self.L.lyon_cuda_flatten_paths_count(self.ctx, ctypes.byref(cb), tolerance, ctypes.byref(nv), ctypes.byref(npt))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        out = DeviceBatch.__new__(DeviceBatch)
+        out.n_paths, out.num_attributes = dbatch.n_paths, 0
+        out.n_verbs, out.n_points = int(nv.value), int(npt.value)
+        out.verbs = torch.empty((out.n_verbs,), dtype=torch.uint8, device=self.device)
+        out.points = torch.empty((2 * out.n_points,), dtype=torch.float32, device=self.device)
+        out.path_verb_begin = torch.empty((dbatch.n_paths + 1,), dtype=torch.int32, device=self.device)
+        out.path_point_begin = torch.empty((dbatch.n_paths + 1,), dtype=torch.int32, device=self.device)
+        st = self.L.lyon_cuda_flatten_paths_emit(self.ctx, out.verbs.data_ptr(), out.points.data_ptr(),
+                                                 out.path_verb_begin.data_ptr(), out.path_point_begin.data_ptr())
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return out
+
     def flatten_curves_fused(self, d_ctrl, npts: int, tolerance: float, with_t: bool = False):
         """Single pass (count + scan + emit in one kernel) into buffers kept across calls; they grow when the batch
         needs more room (one extra pass).  Returns views of the kept buffers, like flatten_curves."""

@@ -88,6 +88,10 @@ extern "C" {
     pub fn lyon_cuda_flatten_quadratics_fused(ctx: *mut lyon_cuda_ctx, d_ctrl: *const f32, n: u64, tolerance: f32,
                                               d_offsets: *mut u64, d_points: *mut f32, point_capacity: u64, d_t: *mut f32,
                                               total_points: *mut u64) -> c_int;
+    pub fn lyon_cuda_flatten_paths_count(ctx: *mut lyon_cuda_ctx, d_batch: *const lyon_path_batch, tolerance: f32,
+                                         n_out_verbs: *mut u64, n_out_points: *mut u64) -> c_int;
+    pub fn lyon_cuda_flatten_paths_emit(ctx: *mut lyon_cuda_ctx, d_out_verbs: *mut u8, d_out_points: *mut f32,
+                                        d_out_path_verb_begin: *mut u32, d_out_path_point_begin: *mut u32) -> c_int;
     pub fn lyon_cuda_rebase_indices(ctx: *mut lyon_cuda_ctx, d_indices: *mut u32, n_indices: u64, n_vertices: u64,
                                     vertex_base: u64) -> c_int;
     pub fn lyon_cuda_set_pipeline(ctx: *mut lyon_cuda_ctx, pipeline: c_int) -> c_int;

@@ -209,6 +209,34 @@ def test_vertex_base_and_too_many_vertices(tz):
         gpu_stroke(tz, batch, o, vertex_base=0xFFFFFFFE)
 
 
+def test_flatten_paths(tz, route):
+    """The path-level `Flattened` adapter (iterator.rs:125-226) on the device against the oracle: same verbs, same
+    points byte for byte, same ranges; and the flattened batch strokes like the original does with Bevel joins...
+    (it is a valid batch for every entry point)."""
+    if route != "tile":
+        pytest.skip("one route")
+    import torch
+    for batch in (W.random_small_paths(500, 21, degenerate=0.1), W.c3_mixed_paths(2000, 64, seed=4, closed_fraction=0.3),
+                  PathBatch.from_paths(W.fixture_paths(GOLDEN)), PathBatch.from_paths([Path.builder().build()])):
+        for tol in (0.5, 0.05, 0.002):
+            d = tz.upload(batch)
+            out = tz.flatten_paths(d, tol)
+            torch.cuda.synchronize()
+            want = O.flatten_paths(batch, tol)
+            assert np.array_equal(out.verbs.cpu().numpy(), want.verbs)
+            assert out.points.cpu().numpy().tobytes() == np.ascontiguousarray(want.points, np.float32).tobytes()
+            assert np.array_equal(out.path_verb_begin.cpu().numpy().astype(np.uint32), want.path_verb_begin)
+            assert np.array_equal(out.path_point_begin.cpu().numpy().astype(np.uint32), want.path_point_begin)
+    # the flattened batch is itself a batch: stroke it on the device and with the oracle
+    batch = W.c3_mixed_paths(300, 16, seed=8)
+    out = tz.flatten_paths(tz.upload(batch), 0.1)
+    o = StrokeOptions(line_join=LineJoin.Bevel)
+    v, i = tz.stroke(out, o)
+    torch.cuda.synchronize()
+    from lyon_b200 import device_mesh_to_host
+    assert_mesh_parity(device_mesh_to_host(v, i), O.stroke_batch(O.flatten_paths(batch, 0.1), o), bbox_extent(batch))
+
+
 def test_rebase_indices(tz, route):
     """lyon_cuda_rebase_indices: a mesh emitted with local ids, rebased afterwards == emitted with the base (the
     multi-GPU single-pass flow), for every alignment of the index buffer."""
