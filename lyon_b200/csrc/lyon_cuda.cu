@@ -38,6 +38,9 @@ constexpr int WARPS = BLOCK / 32;
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint64_t ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, VAL_MASK = (1ull << 62) - 1ull;
 
+#ifdef LYON_PHASE_TIMING
+__device__ unsigned long long g_lookback_stats[4];
+#endif
 __device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -69,9 +72,15 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t 
     for (;;) {
         int64_t idx = look - (int64_t)lane;
         uint64_t d = ST_PREFIX;  // tiles before the first one: prefix 0
+#ifdef LYON_PHASE_TIMING
+        if (lane == 0u) atomicAdd(&g_lookback_stats[0], 1ull);  // windows
+#endif
         if (idx >= 0) {
             d = ld_desc(&desc[idx]);
             while ((d >> 62) == 0ull) {
+#ifdef LYON_PHASE_TIMING
+                atomicAdd(&g_lookback_stats[1], 1ull);  // polls of a descriptor that was not ready
+#endif
                 __nanosleep(64);
                 d = ld_desc(&desc[idx]);
             }
@@ -88,6 +97,71 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t 
     }
     if (lane == 0u) st_desc(&desc[tile], ST_PREFIX | (excl + aggregate));
     return excl;
+}
+// The two look-backs of a stroke tile (vertex and triangle descriptors) advanced together: both descriptors of a
+// predecessor are loaded in the same round trip.  Each array keeps its own state (a predecessor's two descriptors are
+// two stores and may be observed in different states).  Called by all 32 lanes of ONE warp.
+__device__ __forceinline__ void lookback_exclusive_pair(uint64_t* desc_a, uint64_t* desc_b, uint32_t tile, uint64_t agg_a,
+                                                        uint64_t agg_b, uint64_t* excl_a, uint64_t* excl_b) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0u) {
+        if (lane == 0u) {
+            st_desc(&desc_a[0], ST_PREFIX | agg_a);
+            st_desc(&desc_b[0], ST_PREFIX | agg_b);
+        }
+        *excl_a = *excl_b = 0ull;
+        return;
+    }
+    if (lane == 0u) {
+        st_desc(&desc_a[tile], ST_AGG | agg_a);
+        st_desc(&desc_b[tile], ST_AGG | agg_b);
+    }
+    uint64_t ea = 0ull, eb = 0ull;
+    bool done_a = false, done_b = false;
+    int64_t look = (int64_t)tile - 1;
+    for (;;) {
+        const int64_t idx = look - (int64_t)lane;
+        uint64_t da = ST_PREFIX, db = ST_PREFIX;  // tiles before the first one: prefix 0
+        if (idx >= 0) {
+            if (!done_a) da = ld_desc(&desc_a[idx]);
+            if (!done_b) db = ld_desc(&desc_b[idx]);
+            while ((da >> 62) == 0ull || (db >> 62) == 0ull) {
+                __nanosleep(64);
+                if ((da >> 62) == 0ull) da = ld_desc(&desc_a[idx]);
+                if ((db >> 62) == 0ull) db = ld_desc(&desc_b[idx]);
+            }
+        }
+        if (!done_a) {
+            const unsigned pmask = __ballot_sync(0xffffffffu, (da >> 62) == 2ull);
+            const uint64_t val = da & VAL_MASK;
+            if (pmask) {
+                const unsigned first = (unsigned)__ffs((int)pmask) - 1u;
+                ea += warp_sum_u64(lane <= first ? val : 0ull);
+                done_a = true;
+            } else {
+                ea += warp_sum_u64(val);
+            }
+        }
+        if (!done_b) {
+            const unsigned pmask = __ballot_sync(0xffffffffu, (db >> 62) == 2ull);
+            const uint64_t val = db & VAL_MASK;
+            if (pmask) {
+                const unsigned first = (unsigned)__ffs((int)pmask) - 1u;
+                eb += warp_sum_u64(lane <= first ? val : 0ull);
+                done_b = true;
+            } else {
+                eb += warp_sum_u64(val);
+            }
+        }
+        if (done_a && done_b) break;
+        look -= 32;
+    }
+    if (lane == 0u) {
+        st_desc(&desc_a[tile], ST_PREFIX | (ea + agg_a));
+        st_desc(&desc_b[tile], ST_PREFIX | (eb + agg_b));
+    }
+    *excl_a = ea;
+    *excl_b = eb;
 }
 // Block-wide exclusive scan of one u32 per thread. Returns the thread's exclusive prefix; *total = block sum.
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s_warp /*[WARPS+1]*/, uint32_t* total) {
@@ -1161,8 +1235,30 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     if (!tile_config(c, c->h_tile_totals->max_path_slots, total, &g, &q)) return LYON_OK;
     const uint32_t s_cap = g.s_cap, w_v = g.w_v, w_t = g.w_t;
     c->tile_nt = g.nt;
-    const unsigned long long n_tiles64 = total / q + 1ull;
-    if (n_tiles64 > 0x7FFFFFFFull) return LYON_OK;
+    // tile table: greedy packing inside coarse blocks (k_tile_pack), two passes around a scan of the per-block counts
+    const uint32_t max_path = c->h_tile_totals->max_path_slots ? c->h_tile_totals->max_path_slots : 1u;
+    uint32_t cap = q + max_path - 1u;  // what a tile of the quantum `q` could hold at most (q shrinks for small batches)
+    if (cap > s_cap) cap = s_cap;
+    const unsigned long long qc = 32ull * cap;
+    const unsigned long long n_blocks64 = total / qc + 1ull;
+    if (n_blocks64 > 0x3FFFFFFFull) return LYON_OK;
+    const uint32_t n_blocks = (uint32_t)n_blocks64;
+    TRY(ensure(c, c->vw_nv, ((size_t)n_blocks + 1) * 4));
+    TRY(ensure(c, c->vw_v0, ((size_t)n_blocks + 1) * 8));
+    const unsigned btiles = grid_for(n_blocks, BLOCK * 4);
+    TRY(ensure(c, c->desc, (size_t)btiles * 8));
+    TRY(ensure(c, c->misc, 512));
+    CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)btiles * 8, c->stream));
+    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, n_blocks,
+                                                               (uint32_t*)c->vw_nv.p, nullptr, nullptr);
+    k_scan_counts<<<btiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, n_blocks, (unsigned long long*)c->vw_v0.p,
+                                                  d_ticket(c, 0), (uint64_t*)c->desc.p);
+    unsigned long long n_tiles64 = 0ull;
+    CU_TRY(c, cudaMemcpyAsync(&n_tiles64, (unsigned long long*)c->vw_v0.p + n_blocks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    if (n_tiles64 == 0ull || n_tiles64 > 0x7FFFFFFFull) return LYON_OK;
     c->tile_n_tiles = (uint32_t)n_tiles64;
     c->tile_s_cap = s_cap;
     c->tile_w_v = w_v;
@@ -1171,8 +1267,8 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     TRY(ensure(c, c->tile_first, ((size_t)c->tile_n_tiles + 1) * 4));
     TRY(ensure(c, c->tile_desc, (size_t)c->tile_n_tiles * 16));
     TRY(ensure(c, c->tile_base, (size_t)c->tile_n_tiles * 16));
-    k_tile_bounds<<<grid_for((uint64_t)np + 1, 256), 256, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, q,
-                                                                         c->tile_n_tiles, (uint32_t*)c->tile_first.p);
+    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, n_blocks,
+                                                               nullptr, (const unsigned long long*)c->vw_v0.p, (uint32_t*)c->tile_first.p);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     c->tile_batch = *b;
@@ -1839,6 +1935,14 @@ extern "C" int lyon_cuda_debug_phase_cycles(lyon_cuda_ctx* c, uint64_t* out16) {
     if (!c || !out16) return LYON_ERR_INVALID_ARGUMENT;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaMemcpyFromSymbol(out16, g_phase_cycles, 16 * sizeof(uint64_t)));
+    {
+        unsigned long long st[4];
+        CU_TRY(c, cudaMemcpyFromSymbol(st, g_lookback_stats, sizeof(st)));
+        out16[14] = st[0];
+        out16[15] = st[1];
+        static const unsigned long long z[4] = {0, 0, 0, 0};
+        CU_TRY(c, cudaMemcpyToSymbol(g_lookback_stats, z, sizeof(z)));
+    }
     static const uint64_t zero[16] = {0};
     CU_TRY(c, cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
     return LYON_OK;

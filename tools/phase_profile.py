@@ -40,8 +40,6 @@ def main():
     print(f"paths {n} vertices {v.shape[0]} kernel {ms:.3f} ms")
     for k, name in enumerate(NAMES):
         print(f"  {name:18s} {out[k] / tot * 100:6.2f} %   {out[k]:>14d} cycles")
-    if out[12] and out[14]:
-        print(f"  emit loop per warp: joins {out[11] / out[12]:.0f} cycles ({out[12]} warps), Ends {out[13] / out[14]:.0f} cycles ({out[14]} warps)")
 
 
 if __name__ == "__main__":
