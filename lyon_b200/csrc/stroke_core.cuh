@@ -652,21 +652,23 @@ LYC_HD uint32_t arc_subdivisions(float diff, float radius, const StrokeParams& o
     return round_log2_segments(num_segments);
 }
 
-// tessellate_round_join (stroke.rs:1968-2021).  SIDE is a compile-time constant at every call site.
-template <int SIDE, class Sink>
-LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Join& j, const StrokeParams& o) {
+// tessellate_round_join (stroke.rs:1968-2021).  `negative` is a run-time value: in a warp the front side of the joins
+// is Positive for some lanes and Negative for the others, and one code path keeps them all busy (the side's fields are
+// picked with selects, so the Join stays in registers).
+template <class Sink>
+LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Join& j, const StrokeParams& o, bool negative) {
     V2 center = vt.position_on_path;
     float radius = vt.half_width;
-    V2 start_normal = j.prev[SIDE] - center;
-    V2 end_normal = j.next[SIDE] - center;
-    uint32_t start_vertex = j.prev_v[SIDE];
-    uint32_t end_vertex = j.next_v[SIDE];
-    float angle_sign = SIDE == SIDE_NEGATIVE ? 1.0f : -1.0f;
+    V2 start_normal = (negative ? j.prev[SIDE_NEGATIVE] : j.prev[SIDE_POSITIVE]) - center;
+    V2 end_normal = (negative ? j.next[SIDE_NEGATIVE] : j.next[SIDE_POSITIVE]) - center;
+    uint32_t start_vertex = negative ? j.prev_v[SIDE_NEGATIVE] : j.prev_v[SIDE_POSITIVE];
+    uint32_t end_vertex = negative ? j.next_v[SIDE_NEGATIVE] : j.next_v[SIDE_POSITIVE];
+    float angle_sign = negative ? 1.0f : -1.0f;
     float start_angle = angle_from_x_axis(start_normal);
     float diff = angle_to(start_angle, angle_from_x_axis(end_normal));
     if (diff * angle_sign < 0.0f) diff = angle_sign * (2.0f * LYC_PI_F - fabsf(diff));
     float end_angle = start_angle + diff;
-    if (SIDE == SIDE_NEGATIVE) {
+    if (negative) {
         float ta = start_angle;
         start_angle = end_angle;
         end_angle = ta;
@@ -675,7 +677,7 @@ LYC_HD void tessellate_round_join(Sink& sink, const VertexTemplate& vt, const Jo
         end_vertex = tv;
     }
     uint32_t k = arc_subdivisions(diff, radius, o);
-    emit_arc(sink, vt, SIDE != SIDE_POSITIVE, start_angle, end_angle, start_vertex, end_vertex, k);
+    emit_arc(sink, vt, negative, start_angle, end_angle, start_vertex, end_vertex, k);
 }
 
 // tessellate_join (stroke.rs:1907-1965)
@@ -694,8 +696,12 @@ LYC_HD void tessellate_join(Sink& sink, const VertexTemplate& vt, const Join& j,
         }
     }
     if (j.line_join == JOIN_ROUND) {
-        if (need0) tessellate_round_join<SIDE_POSITIVE>(sink, vt, j, o);
-        if (need1) tessellate_round_join<SIDE_NEGATIVE>(sink, vt, j, o);
+        if (need0 != need1) {  // the usual case: only the front side
+            tessellate_round_join(sink, vt, j, o, need1);
+        } else if (need0) {  // Positive first, then Negative (stroke.rs:1954-1963)
+            tessellate_round_join(sink, vt, j, o, false);
+            tessellate_round_join(sink, vt, j, o, true);
+        }
     }
 }
 

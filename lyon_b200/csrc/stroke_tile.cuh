@@ -147,34 +147,53 @@ LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t ver
 // endpoint); the previous sample of the same curve is re-evaluated rather than read, so the phase needs no ordering.
 LYC_HD void tile_eval_slot(const TileViews& w, const StrokeParams& p, const V2* points, uint32_t s) {
     const uint8_t fl = w.flags[s];
-    const uint32_t pt = f2u(w.adv[s]);
-    if (fl & TF_EVAL) {
-        const float t = w.t[s];
-        const V2 from = seg_from_point(points, pt, p.attr_stride);
-        V2 pos, prev;
-        if (fl & TF_CUBIC) {
-            const V2 to = points[pt + 2];
-            const CubicPoly poly = cubic_poly(from, points[pt], points[pt + 1], to);
-            pos = (fl & TF_LAST) ? to : cubic_poly_sample(poly, t);
-            prev = (fl & TF_FIRST) ? from : cubic_poly_sample(poly, w.t[s - 1u]);
-        } else {
-            const V2 to = points[pt + 1];
-            const QuadPoly poly = quad_poly(from, points[pt], to);
-            pos = (fl & TF_LAST) ? to : quad_poly_sample(poly, t);
-            prev = (fl & TF_FIRST) ? from : quad_poly_sample(poly, w.t[s - 1u]);
-        }
-        w.pos[s] = pos;
-        w.len()[s] = tile_len_flagged(p, pos, prev);
-    } else if (fl & TF_BEGIN) {
-        w.pos[s] = points[pt];
-        w.len()[s] = 0.0f;
-    } else if (fl & TF_END) {
+    if (fl & TF_END) {
         w.len()[s] = 0.0f;  // pos/adv are written by tile_path_walk (sub-path record)
-    } else if (fl & TF_CUBIC) {  // line endpoint
-        const V2 pos = points[pt];
-        w.pos[s] = pos;
-        w.len()[s] = tile_len_flagged(p, pos, seg_from_point(points, pt, p.attr_stride));
+        return;
     }
+    if (!(fl & (TF_EVAL | TF_BEGIN | TF_CUBIC))) return;  // finished in phase 1a (split quadratic)
+    // One code path for Begin, line endpoints and curve samples: the point is either the verb's last stored point
+    // (`to`) or a sample of the polynomial form; only the coefficients differ between quadratics and cubics.
+    const uint32_t pt = f2u(w.adv[s]);
+    const bool curve = (fl & TF_EVAL) != 0, cubic = curve && (fl & TF_CUBIC) != 0;
+    const uint32_t npts = cubic ? 3u : (curve ? 2u : 1u);
+    const V2 to = points[pt + npts - 1u];
+    const V2 from = (fl & TF_BEGIN) ? to : seg_from_point(points, pt, p.attr_stride);
+    const bool first = !curve || (fl & TF_FIRST) != 0, last = !curve || (fl & TF_LAST) != 0;
+    V2 pos = to, prev = from;
+    if (!(first && last)) {
+        const float t = w.t[s];
+        const float tp = first ? 0.0f : w.t[s - 1u];
+        const V2 c1 = points[pt];
+        V2 a1, a2, a3 = v2(0.0f, 0.0f);
+        if (cubic) {
+            const CubicPoly q = cubic_poly(from, c1, points[pt + 1], to);
+            a1 = q.a1;
+            a2 = q.a2;
+            a3 = q.a3;
+        } else {
+            const QuadPoly q = quad_poly(from, c1, to);
+            a1 = q.a1;
+            a2 = q.a2;
+        }
+        // Horner as the reference has it: v = a0; v += a1*t; v += a2*t^2; [v += a3*t^3] -- for t and for the previous t
+        float u = t, up = tp;
+        V2 v = from + a1 * u, vp = from + a1 * up;
+        u = u * t;
+        up = up * tp;
+        v = v + a2 * u;
+        vp = vp + a2 * up;
+        if (cubic) {
+            u = u * t;
+            up = up * tp;
+            v = v + a3 * u;
+            vp = vp + a3 * up;
+        }
+        if (!last) pos = v;
+        if (!first) prev = vp;
+    }
+    w.pos[s] = pos;
+    w.len()[s] = (fl & TF_BEGIN) ? 0.0f : tile_len_flagged(p, pos, prev);
 }
 // Phase 1c: a slot is "special" for the walk when it is not an ordinary kept point: Begin, End, or possibly within
 // the merge distance of its predecessor.
