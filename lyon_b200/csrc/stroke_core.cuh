@@ -715,21 +715,26 @@ LYC_HD void emit_join_vertices(Sink& sink, const VertexTemplate& vt, Join& j) {
         j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = nv;
         return;
     }
-    // add_join_base_vertices, stroke.rs:2024-2055: Negative side first, then Positive
-    if (j.has_single[SIDE_NEGATIVE]) {
-        uint32_t id = sink.add_vertex(vt, (j.single[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
-        j.prev_v[SIDE_NEGATIVE] = j.next_v[SIDE_NEGATIVE] = id;
-    } else {
-        j.prev_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (j.prev[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
-        j.next_v[SIDE_NEGATIVE] = sink.add_vertex(vt, (j.next[SIDE_NEGATIVE] - vt.position_on_path) / vt.half_width, true);
+    // add_join_base_vertices, stroke.rs:2024-2055: Negative side first, then Positive; a side is one vertex (single) or
+    // two (prev, next).  Written as "vertex 0, 1, 2[, 3]" with the position picked by selects, so that the lanes of a
+    // warp -- whose joins differ in which side is the single one -- all emit their i-th vertex together.
+    const uint32_t base = sink.next_id();
+    const bool sn = j.has_single[SIDE_NEGATIVE], sp = j.has_single[SIDE_POSITIVE];
+    const V2 c = vt.position_on_path;
+    const float hw = vt.half_width;
+    const V2 n0 = sn ? j.single[SIDE_NEGATIVE] : j.prev[SIDE_NEGATIVE];
+    const V2 p0 = sp ? j.single[SIDE_POSITIVE] : j.prev[SIDE_POSITIVE];
+    sink.add_vertex(vt, (n0 - c) / hw, true);
+    {
+        const V2 q = sn ? p0 : j.next[SIDE_NEGATIVE];
+        sink.add_vertex(vt, (q - c) / hw, !sn);
     }
-    if (j.has_single[SIDE_POSITIVE]) {
-        uint32_t id = sink.add_vertex(vt, (j.single[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
-        j.prev_v[SIDE_POSITIVE] = j.next_v[SIDE_POSITIVE] = id;
-    } else {
-        j.prev_v[SIDE_POSITIVE] = sink.add_vertex(vt, (j.prev[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
-        j.next_v[SIDE_POSITIVE] = sink.add_vertex(vt, (j.next[SIDE_POSITIVE] - vt.position_on_path) / vt.half_width, false);
+    if (!sn || !sp) {
+        const V2 q = sn ? j.next[SIDE_POSITIVE] : p0;
+        sink.add_vertex(vt, (q - c) / hw, false);
     }
+    if (!sn && !sp) sink.add_vertex(vt, (j.next[SIDE_POSITIVE] - c) / hw, false);
+    join_assign_ids(j, base);
 }
 
 // tessellate_round_cap (stroke.rs:2459-2524)
