@@ -283,8 +283,8 @@ def main():
         "bound": "hbm", "kernel": "k_stroke_tile<FUSED>", "achieved": k_gbs,
         "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: ncu --set full on the first 200k paths of the same
-        # batch measured 9.679 GB for 8.686 GB of algorithmic bytes (profiles/r01j_ncu_summary.txt); scaled to this launch
-        "traffic": int(alg_bytes * (9.679 / 8.686)), "traffic_source": "ncu capture on a 200k-path sample, scaled by algorithmic bytes",
+        # batch measured 9.647 GB for 8.686 GB of algorithmic bytes (profiles/r01k_ncu_summary.txt); scaled to this launch
+        "traffic": int(alg_bytes * (9.647 / 8.686)), "traffic_source": "ncu capture on a 200k-path sample, scaled by algorithmic bytes",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms": dev_ms / args.steps,
         "kernel_share_of_step": k_ms / (dev_ms / args.steps),
         "whole_step_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
@@ -380,7 +380,7 @@ def bench_flatten(tz, torch, dev, peak, args):
             "roofline": {"bound": "hbm", "kernel": "k_flat_emit<4, fused>", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg,
-                         # ncu --set full, same launch: 0.320 GB read + 1.974 GB written (profiles/r01j_ncu_summary.txt)
+                         # ncu --set full, same launch: 0.320 GB read + 1.974 GB written (profiles/r01k_ncu_summary.txt)
                          "traffic": 2294213176}}
 
 
