@@ -1239,7 +1239,11 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     const uint32_t max_path = c->h_tile_totals->max_path_slots ? c->h_tile_totals->max_path_slots : 1u;
     uint32_t cap = q + max_path - 1u;  // what a tile of the quantum `q` could hold at most (q shrinks for small batches)
     if (cap > s_cap) cap = s_cap;
-    const unsigned long long qc = 32ull * cap;
+    // coarse block = what one thread packs: 32 tiles' worth of slots, fewer for small batches (the packing of a block is
+    // sequential, and a batch of a few hundred tiles should still spread over many threads)
+    unsigned long long qc = 32ull * cap;
+    if (total / 512ull < qc) qc = total / 512ull;
+    if (qc < 2ull * cap) qc = 2ull * cap;
     const unsigned long long n_blocks64 = total / qc + 1ull;
     if (n_blocks64 > 0x3FFFFFFFull) return LYON_OK;
     const uint32_t n_blocks = (uint32_t)n_blocks64;
