@@ -1166,12 +1166,17 @@ struct TileGeom {
 // Default: 256 threads and 3520 slots per CTA, two CTAs per SM (each hides the other's serial phases; measured
 // best on C3, see profiles/).  Longer paths: one 512-thread CTA per SM with all its shared memory (~7000 slots).
 // The tile quantum shrinks for small batches so that every SM still gets a few tiles.  LYON_TILE=nt,cap,0 overrides.
+#ifdef LYON_DEV_BUILD  // experiment builds launch one fixed instantiation (LYON_DEV_NT): LYON_TILE may name any warp multiple
+bool dev_nt_ok(unsigned nt) { return nt >= 64u && nt <= 1024u && (nt & 31u) == 0u; }
+#else
+bool dev_nt_ok(unsigned) { return false; }
+#endif
 bool tile_config(const lyon_cuda_ctx* c, uint32_t max_path, unsigned long long total, TileGeom* g, uint32_t* quantum) {
     TileGeom pick{};
     bool found = false;
     if (const char* e = getenv("LYON_TILE")) {
         unsigned nt = 0, cap = 0, wv = 0;
-        if (sscanf(e, "%u,%u,%u", &nt, &cap, &wv) == 3 && (nt == 128 || nt == 256 || nt == 257 || nt == 512) && cap >= 64) {
+        if (sscanf(e, "%u,%u,%u", &nt, &cap, &wv) == 3 && (nt == 128 || nt == 256 || nt == 257 || nt == 512 || dev_nt_ok(nt)) && cap >= 64) {
             pick = TileGeom{(int)nt, cap & ~31u, 0u, 0u};
             found = max_path <= pick.s_cap;
         }

@@ -93,6 +93,56 @@ LYC_HD uint32_t tile_gen_quad_half(const TileViews& w, const StrokeParams& p, ui
     return cnt;
 }
 
+// One quadratic that flatten_quad splits at a sharp turn (stroke.rs:2755-2779), its slots dealt round-robin: this call
+// writes slots j0, j0 + stride, ... of the verb (tile kernel: one WARP per split quadratic, j0 = lane, stride = 32, instead
+// of one lane of the verb phase running both halves alone; tests/emul: every j0 of a stride).  A slot replays the
+// accumulated parameter of its half from t = 0 (one FADD per earlier slot, continuing from the caller's previous slot
+// while it stays in the same half) and re-evaluates its predecessor's position from the predecessor's t, so the slots
+// are independent of each other and bit-identical to the sequential tile_gen_quad_half.
+LYC_HD void tile_gen_split_quad(const TileViews& w, const StrokeParams& p, const V2* points, uint32_t pt, uint32_t s0,
+                                uint32_t src, uint32_t j0, uint32_t stride) {
+    const VerbPlan plan = plan_verb(VERB_QUAD, points, pt, p.attr_stride, p.tolerance);
+    if (!(plan.tsplit >= 0.0f)) return;  // the pre-pass found a split: cannot happen
+    const V2 from = seg_from_point(points, pt, p.attr_stride);
+    const V2 ctrl = points[pt], to = points[pt + 1];
+    const float tsplit = plan.tsplit;
+    const V2 sp = quad_sample(from, ctrl, to, tsplit);
+    const uint32_t cnt_a = to_u32_or_1(plan.n_a), cnt_b = to_u32_or_1(plan.n_b);
+    const QuadPoly poly_a = quad_poly(from, lerp(from, ctrl, tsplit), sp), poly_b = quad_poly(sp, lerp(ctrl, to, tsplit), to);
+    const float step_a = 1.0f / plan.n_a, step_b = 1.0f / plan.n_b;
+    const unsigned long long total = (unsigned long long)cnt_a + cnt_b;
+    bool in_b = false;
+    uint32_t k_done = 0u;  // additions replayed so far in the current half
+    float t = 0.0f;        // the half's accumulated parameter after k_done additions
+    for (unsigned long long j = j0; j < total; j += stride) {
+        const bool hb = j >= cnt_a;
+        const uint32_t k = (uint32_t)(hb ? j - cnt_a : j);
+        if (hb != in_b) {
+            in_b = hb;
+            k_done = 0u;
+            t = 0.0f;
+        }
+        const float step = hb ? step_b : step_a;
+        const uint32_t cnt = hb ? cnt_b : cnt_a;
+        while (k_done < k) {
+            t = t + step;
+            ++k_done;
+        }
+        const V2 prev = k == 0u ? (hb ? sp : from) : quad_poly_sample(hb ? poly_b : poly_a, t);
+        V2 pos;
+        float ts;
+        if (k + 1u < cnt) {
+            ts = t + step;
+            pos = quad_poly_sample(hb ? poly_b : poly_a, ts);
+        } else {
+            ts = 1.0f;
+            pos = hb ? to : sp;
+        }
+        const float t_out = hb ? tsplit + ts * (1.0f - tsplit) : ts * tsplit;
+        tile_put_slot(w, p, s0 + (uint32_t)j, pos, prev, true, t_out, ts != 1.0f ? TF_FS : 0, src);
+    }
+}
+
 // Phase 1a (thread per verb): every slot of verb `verb` (first stored point `pt`, first slot s0, EndpointId `src`).
 // Only the SEQUENTIAL part of a verb runs here -- the accumulated parameter t1 = t0 + step of
 // for_each_flattened_with_t (cubic_bezier.rs:605-611, quadratic_bezier.rs:382-388) -- and every slot is left with its

@@ -15,8 +15,8 @@ import torch  # noqa: E402
 import workloads as W  # noqa: E402
 from lyon_b200 import DeviceTessellator, LineCap, LineJoin, StrokeOptions  # noqa: E402
 
-NAMES = ["0 ticket", "0 stage + 1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
-         "6 fast emit", "6 full/end emit"]
+NAMES = ["0 ticket", "1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
+         "6 fast emit", "6 full/end emit", "0 stage (TMA wait)"]
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
     torch.cuda.synchronize()
     ms = tz.last_kernel_ms()
     tz.L.lyon_cuda_debug_phase_cycles(tz.ctx, out)
-    tot = sum(out[:11])
+    tot = sum(out[:12])
     print(f"paths {n} vertices {v.shape[0]} kernel {ms:.3f} ms")
     for k, name in enumerate(NAMES):
         print(f"  {name:18s} {out[k] / tot * 100:6.2f} %   {out[k]:>14d} cycles")
