@@ -1166,6 +1166,11 @@ struct TileGeom {
 // Default: 256 threads and 3520 slots per CTA, two CTAs per SM (each hides the other's serial phases; measured
 // best on C3, see profiles/).  Longer paths: one 512-thread CTA per SM with all its shared memory (~7000 slots).
 // The tile quantum shrinks for small batches so that every SM still gets a few tiles.  LYON_TILE=nt,cap,0 overrides.
+#ifdef LYON_DEV_NT
+#define LYON_DEV_NT_OR_DEFAULT LYON_DEV_NT
+#else
+#define LYON_DEV_NT_OR_DEFAULT 256
+#endif
 #ifdef LYON_DEV_BUILD  // experiment builds launch one fixed instantiation (LYON_DEV_NT): LYON_TILE may name any warp multiple
 bool dev_nt_ok(unsigned nt) { return nt >= 64u && nt <= 1024u && (nt & 31u) == 0u; }
 #else
@@ -1247,6 +1252,12 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     // coarse block = what one thread packs: 32 tiles' worth of slots, fewer for small batches (the packing of a block is
     // sequential, and a batch of a few hundred tiles should still spread over many threads)
     unsigned long long qc = 32ull * cap;
+#ifdef LYON_DEV_BUILD
+    uint32_t group = (uint32_t)LYON_DEV_NT_OR_DEFAULT / 32u;
+#else
+    uint32_t group = (uint32_t)(g.nt & ~31) / 32u;
+#endif
+    if (const char* e = getenv("LYON_TILE_GROUP")) group = (uint32_t)atoi(e);  // experiments: 0 switches the trimming off
     if (total / 512ull < qc) qc = total / 512ull;
     if (qc < 2ull * cap) qc = 2ull * cap;
     const unsigned long long n_blocks64 = total / qc + 1ull;
@@ -1259,7 +1270,7 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     TRY(ensure(c, c->misc, 512));
     CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)btiles * 8, c->stream));
-    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, n_blocks,
+    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, group, n_blocks,
                                                                (uint32_t*)c->vw_nv.p, nullptr, nullptr);
     k_scan_counts<<<btiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, n_blocks, (unsigned long long*)c->vw_v0.p,
                                                   d_ticket(c, 0), (uint64_t*)c->desc.p);
@@ -1276,7 +1287,7 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     TRY(ensure(c, c->tile_first, ((size_t)c->tile_n_tiles + 1) * 4));
     TRY(ensure(c, c->tile_desc, (size_t)c->tile_n_tiles * 16));
     TRY(ensure(c, c->tile_base, (size_t)c->tile_n_tiles * 16));
-    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, n_blocks,
+    k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, group, n_blocks,
                                                                nullptr, (const unsigned long long*)c->vw_v0.p, (uint32_t*)c->tile_first.p);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
