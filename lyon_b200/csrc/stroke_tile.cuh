@@ -251,6 +251,24 @@ LYC_HD bool tile_slot_special(const TileViews& w, uint32_t s) {
     return (w.flags[s] & (TF_BEGIN | TF_END)) != 0 || len_flagged(w.len()[s]);
 }
 
+// Phase 1d: a flagged ("maybe mergeable") slot whose predecessor is certainly kept -- an ordinary point or a Begin -- is
+// compared by the merge filter (stroke.rs:1530-1536) against exactly that predecessor, so the decision is local.  When
+// the pair is NOT within the merge distance the slot is an ordinary kept point after all: its length loses the flag
+// and the caller clears its special bit, so it no longer interrupts the walk's 32-point steps.  Slots may be resolved
+// concurrently: a neighbour seen still flagged only leaves this slot to the walk's general step (same result).
+LYC_HD bool tile_resolve_flagged(const TileViews& w, const StrokeParams& p, uint32_t s) {
+    if (s == 0u) return false;
+    if (w.flags[s] & (TF_BEGIN | TF_END)) return false;
+    if (!len_flagged(w.len()[s])) return false;
+    const uint8_t fp = w.flags[s - 1u];
+    if (fp & TF_END) return false;
+    if (!(fp & TF_BEGIN) && len_flagged(w.len()[s - 1u])) return false;
+    const V2 pl = w.pos[s - 1u], ps = w.pos[s];
+    if (!(sqlen(pl - ps) >= p.merge_thr)) return false;  // merged (or NaN): the walk decides
+    w.len()[s] = length(ps - pl);
+    return true;
+}
+
 // Phase 2: one path = slots [sa, sb) of the tile, sequential.  Same chains as path_walk (stroke_core.cuh):
 // merge filter against the last kept point (stroke.rs:1318-1320, 1530-1536), advancement (stroke.rs:1546-1550,
 // 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), may_need_empty_cap (stroke.rs:1180,

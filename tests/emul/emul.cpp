@@ -186,6 +186,13 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     std::vector<uint32_t> special(NS / 32 + 2, 0);
     for (uint32_t s = 0; s < NS; ++s)
         if (tile_slot_special(w, s)) special[s >> 5] |= 1u << (s & 31u);
+    // phase 1d: flagged slots that are ordinary kept points after all.  Every other candidate is resolved in a first
+    // sweep and the rest in a second one, so both "neighbour already resolved" and "neighbour still flagged" occur
+    // (on the device the order is arbitrary).
+    for (uint32_t pass = 0; pass < 2u; ++pass)
+        for (uint32_t s = 0; s < NS; ++s)
+            if (((special[s >> 5] >> (s & 31u)) & 1u) && ((s & 1u) == pass) && tile_resolve_flagged(w, p, s))
+                special[s >> 5] &= ~(1u << (s & 31u));
     // phase 2: per path
     for (uint32_t path = 0; path < b->n_paths; ++path) {
         uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
