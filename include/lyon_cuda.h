@@ -163,6 +163,15 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, c
 int lyon_cuda_rebase_indices(lyon_cuda_ctx* ctx, uint32_t* d_indices, uint64_t n_indices, uint64_t n_vertices,
                              uint64_t vertex_base);
 
+/* StrokeVertex::interpolated_attributes (stroke.rs:2728-2747) for every vertex of a mesh tessellated from d_batch (paths
+ * built with num_attributes > 0, ids = offsets in each path's point array, stroke.rs:769-869): what a custom
+ * StrokeVertexConstructor reads (geometry_builder.rs:398-433).  d_out[v * num_attributes + i]: the stored attributes of
+ * the endpoint for VertexSource::Endpoint{id} (Path as AttributeStore, path.rs:650-665), a[i] * (1 - t) + b[i] * t between
+ * the curve's two endpoints for VertexSource::Edge{from, to, t}.  d_path_vertex_end: the per-path vertex ranges that
+ * stroke_emit / stroke_fused returned (relative to d_vertices[0]).  A batch without attributes is a no-op. */
+int lyon_cuda_interpolate_attributes(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, const lyon_stroke_vertex* d_vertices,
+                                     uint64_t n_vertices, const uint64_t* d_path_vertex_end, float* d_out);
+
 /* Pipeline selection for plan/emit/fused: 0 = automatic (shared-memory tile pipeline whenever every path of the
  * batch fits a tile), 1 = always the general multi-kernel pipeline (any path length).  Results are identical. */
 int lyon_cuda_set_pipeline(lyon_cuda_ctx* ctx, int pipeline);

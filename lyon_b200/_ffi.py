@@ -31,6 +31,7 @@ SYMBOLS = [
     "lyon_cuda_flatten_cubics_fused", "lyon_cuda_flatten_quadratics_fused",
     "lyon_cuda_flatten_paths_count", "lyon_cuda_flatten_paths_emit",
     "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check", "lyon_cuda_stroke_fused", "lyon_cuda_rebase_indices", "lyon_cuda_set_pipeline",
+    "lyon_cuda_interpolate_attributes",
     "lyon_cuda_enable_timing", "lyon_cuda_last_kernel_ms",
     "lyon_cuda_tessellate_paths", "lyon_cuda_free_host",
 ]
@@ -91,6 +92,7 @@ def lib():
                                          vp, vp, pu64, pu64]
     L.lyon_cuda_rebase_indices.argtypes = [vp, vp, u64, u64, u64]
     L.lyon_cuda_set_pipeline.argtypes = [vp, ctypes.c_int]
+    L.lyon_cuda_interpolate_attributes.argtypes = [vp, ctypes.POINTER(CPathBatch), vp, u64, vp, vp]
     L.lyon_cuda_enable_timing.argtypes = [vp, ctypes.c_int]
     L.lyon_cuda_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.lyon_cuda_tessellate_paths.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions),

@@ -860,6 +860,70 @@ __global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ ver
 
 // Global index rebasing of a mesh emitted with vertex_base 0 (multi-GPU: a rank learns the number of vertices emitted
 // by the ranks before it only after its own single-pass emit): indices[i] += base, 16 bytes per thread and iteration.
+// ---- interpolated attributes (StrokeVertex::interpolated_attributes, stroke.rs:2728-2747) ------------------------------
+// An Edge source names the curve's two endpoints; the vertex keeps `to` and t, and `from` is the endpoint stored before
+// the curve's control points: to - (control points + 1) - attribute slots.  k_attr_curve_kind marks every curve endpoint
+// with its verb's point count (2 quadratic, 3 cubic), one warp per path like the slot pre-pass.
+__global__ void __launch_bounds__(256) k_attr_curve_kind(const uint8_t* __restrict__ verbs, const uint32_t* __restrict__ path_verb_begin,
+                                                         const uint32_t* __restrict__ path_point_begin, uint32_t n_paths,
+                                                         uint32_t attr_stride, uint8_t* __restrict__ kind) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t path = warp; path < n_paths; path += nwarps) {
+        const uint32_t vb = path_verb_begin[path], ve = path_verb_begin[path + 1];
+        uint32_t pt_run = path_point_begin[path];
+        for (uint32_t v0 = vb; v0 < ve; v0 += 32u) {
+            const uint32_t v = v0 + lane;
+            const uint8_t verb = v < ve ? verbs[v] : (uint8_t)VERB_END;
+            const uint32_t npts = v < ve ? verb_point_count(verb, attr_stride) : 0u;
+            uint32_t inc = npts;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (unsigned)o) inc += y;
+            }
+            const uint32_t pt = pt_run + inc - npts;
+            if (verb == VERB_QUAD) kind[pt + 1u] = 2;
+            else if (verb == VERB_CUBIC) kind[pt + 2u] = 3;
+            pt_run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+}
+// One thread per vertex: its path by binary search in the per-path vertex ranges, then Endpoint{id} -> the endpoint's
+// stored attributes (path.rs:650-665), Edge{from, to, t} -> a[i] * (1 - t) + b[i] * t (unfused, like the reference).
+__global__ void __launch_bounds__(256) k_interpolate_attributes(const GpuVertex* __restrict__ vertices, unsigned long long n_vertices,
+                                                                const unsigned long long* __restrict__ path_vertex_end, uint32_t n_paths,
+                                                                const float* __restrict__ points,
+                                                                const uint32_t* __restrict__ path_point_begin,
+                                                                const uint8_t* __restrict__ kind, uint32_t num_attributes,
+                                                                uint32_t attr_stride, float* __restrict__ out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vertices; v += stride) {
+        uint32_t lo = 0u, hi = n_paths;  // first path whose range ends beyond v
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (path_vertex_end[mid] <= v) lo = mid + 1u; else hi = mid;
+        }
+        float* o = out + v * num_attributes;
+        if (lo >= n_paths) {
+            for (uint32_t i = 0; i < num_attributes; ++i) o[i] = 0.0f;
+            continue;
+        }
+        const GpuVertex vx = vertices[v];
+        const unsigned long long to = (unsigned long long)path_point_begin[lo] + (vx.src & 0x7FFFFFFFu);
+        const float* b = points + 2ull * (to + 1ull);
+        if (vx.t == 1.0f) {
+            for (uint32_t i = 0; i < num_attributes; ++i) o[i] = b[i];
+        } else {
+            const unsigned long long from = to - kind[to] - attr_stride;
+            const float* a = points + 2ull * (from + 1ull);
+            const float t = vx.t, one_t = 1.0f - t;
+            for (uint32_t i = 0; i < num_attributes; ++i) o[i] = a[i] * one_t + b[i] * t;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_rebase_indices(uint32_t* __restrict__ idx, unsigned long long n, uint32_t base) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,6 +1053,7 @@ struct lyon_cuda_ctx {
     bool tile_planned = false;            // the last plan went through the tile pipeline
     bool vw_planned = false;              // the last plan went through the variable-width (thread per path) kernels
     DevBuf vw_nv, vw_nt, vw_v0, vw_t0;
+    DevBuf attr_kind;  // lyon_cuda_interpolate_attributes: per point, the point count of the curve ending there
     DevBuf pf_rec;  // path-level flattening: per-verb records (counts reuse vw_nv / vw_nt / vw_v0 / vw_t0)
     bool pf_planned = false;
     lyon_path_batch pf_batch{};
@@ -1488,7 +1553,7 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
-                      &c->pf_rec, &c->vw_nv, &c->vw_nt, &c->vw_v0, &c->vw_t0, &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
+                      &c->pf_rec, &c->attr_kind, &c->vw_nv, &c->vw_nt, &c->vw_v0, &c->vw_t0, &c->verb_n, &c->path_slots, &c->path_events, &c->path_slot_begin, &c->path_event_begin, &c->tile_first, &c->tile_desc, &c->tile_base, &c->tile_misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -1825,6 +1890,32 @@ int lyon_cuda_rebase_indices(lyon_cuda_ctx* c, uint32_t* d_indices, uint64_t n_i
     if (blocks > cap) blocks = cap;
     k_rebase_indices<<<blocks, 256, 0, c->stream>>>(d_indices, n_indices, (uint32_t)vertex_base);
     c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
+int lyon_cuda_interpolate_attributes(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_vertex* d_vertices,
+                                     uint64_t n_vertices, const uint64_t* d_path_vertex_end, float* d_out) {
+    if (!c || !b) return LYON_ERR_INVALID_ARGUMENT;
+    if (b->num_attributes == 0 || n_vertices == 0) return LYON_OK;  // nothing to interpolate
+    if (!d_vertices || !d_path_vertex_end || !d_out || !b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin ||
+        b->n_paths == 0)
+        return LYON_ERR_INVALID_ARGUMENT;
+    const uint32_t attr_stride = (b->num_attributes + 1u) / 2u;
+    TRY(ensure(c, c->attr_kind, (size_t)b->n_points + 16));
+    CU_TRY(c, cudaMemsetAsync(c->attr_kind.p, 0, (size_t)b->n_points + 16, c->stream));
+    unsigned blocks = (b->n_paths + 7u) / 8u;
+    if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
+    k_attr_curve_kind<<<blocks, 256, 0, c->stream>>>(b->verbs, b->path_verb_begin, b->path_point_begin, b->n_paths, attr_stride,
+                                                    (uint8_t*)c->attr_kind.p);
+    unsigned vblocks = grid_for(n_vertices, 256);
+    const unsigned cap = (unsigned)c->num_sms * 32u;
+    if (vblocks > cap) vblocks = cap;
+    k_interpolate_attributes<<<vblocks, 256, 0, c->stream>>>(reinterpret_cast<const GpuVertex*>(d_vertices), n_vertices,
+                                                            (const unsigned long long*)d_path_vertex_end, b->n_paths, b->points,
+                                                            b->path_point_begin, (const uint8_t*)c->attr_kind.p, b->num_attributes,
+                                                            attr_stride, d_out);
+    c->launches += 2;
     CU_TRY(c, cudaGetLastError());
     return LYON_OK;
 }

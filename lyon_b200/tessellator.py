@@ -173,6 +173,18 @@ class DeviceTessellator:
             _raise(self.L, self.ctx, st)
         return indices
 
+    def interpolate_attributes(self, dbatch: DeviceBatch, vertices, path_vertex_end):
+        """StrokeVertex::interpolated_attributes (stroke.rs:2728-2747) of every vertex: float32 [V, num_attributes] on the
+        device.  `vertices` / `path_vertex_end` as returned by stroke(..., with_ranges=True) for the same batch."""
+        torch = self.torch
+        out = torch.empty((vertices.shape[0], dbatch.num_attributes), dtype=torch.float32, device=self.device)
+        cb = dbatch.c_struct()
+        st = self.L.lyon_cuda_interpolate_attributes(self.ctx, ctypes.byref(cb), vertices.data_ptr(), vertices.shape[0],
+                                                     path_vertex_end.data_ptr(), out.data_ptr())
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return out
+
     def set_pipeline(self, general: bool):
         """False: automatic (fused shared-memory tile pipeline when every path fits a tile); True: always the
         general multi-kernel pipeline.  Both produce identical output."""

@@ -331,6 +331,7 @@ enum : int { OK = 0, ERR_TOO_MANY_VERTICES = -2 };
 // BuffersBuilder<_, u32> mirror (geometry_builder.rs:300-351, 451-508, MaxIndex :562-603)
 struct Buffers {
     std::vector<Vertex> vertices;
+    std::vector<uint32_t> vertex_from;  // per vertex: VertexSource::Edge.from (what interpolated_attributes reads, stroke.rs:2735)
     std::vector<uint32_t> indices;
     uint64_t max_index = 0xFFFFFFFEull;  // <u32 as MaxIndex>::MAX: the largest id that may be handed out
     size_t first_vertex = 0, first_index = 0;
@@ -340,6 +341,7 @@ struct Buffers {
     }
     void abort_geometry() {
         vertices.resize(first_vertex);
+        vertex_from.resize(first_vertex);
         indices.resize(first_index);
     }
     bool add_vertex(const Vertex& v, uint32_t* id) {
@@ -368,8 +370,9 @@ struct SidePoints {  // stroke.rs:311-317
     uint32_t prev_vertex, next_vertex;
 };
 struct Source {
-    uint32_t id;  // Endpoint id, or Edge.to
-    float t;      // 1.0 for Endpoint
+    uint32_t id;    // Endpoint id, or Edge.to
+    float t;        // 1.0 for Endpoint
+    uint32_t from;  // Edge.from (lib.rs:282-291); unused for Endpoint sources
 };
 struct EndpointData {  // stroke.rs:320-352
     V2 position;
@@ -388,7 +391,7 @@ static inline EndpointData endpoint_default() {
     e.half_width = nan;
     e.advancement = nan;
     e.line_join = JOIN_MITER;
-    e.src = Source{0xFFFFFFFFu, 1.0f};
+    e.src = Source{0xFFFFFFFFu, 1.0f, 0u};
     for (int s = 0; s < 2; ++s) {
         e.side_points[s].prev = v2(nan, nan);
         e.side_points[s].next = v2(nan, nan);
@@ -470,7 +473,7 @@ public:
         vertex.half_width = o.line_width * 0.5f;
         vertex.advancement = 0.0f;
         vertex.side_negative = true;
-        vertex.src = Source{0xFFFFFFFFu, 1.0f};
+        vertex.src = Source{0xFFFFFFFFu, 1.0f, 0u};
     }
 
     // One path = one `StrokeTessellator::tessellate_path` call (stroke.rs:164-177):
@@ -505,7 +508,7 @@ public:
                     d.position = at;
                     d.advancement = sub_path_start_advancement;
                     d.line_join = options.line_join;
-                    d.src = Source{with_ids ? ep : seq_id, 1.0f};
+                    d.src = Source{with_ids ? ep : seq_id, 1.0f, 0u};
                     if (vw) {
                         d.half_width = base_width * attr(ep) * 0.5f;  // stroke.rs:671
                         step(d);
@@ -525,7 +528,7 @@ public:
                     EndpointData d = endpoint_default();
                     d.position = to;
                     d.line_join = options.line_join;
-                    d.src = Source{with_ids ? ep : seq_id, 1.0f};
+                    d.src = Source{with_ids ? ep : seq_id, 1.0f, 0u};
                     if (vw) {
                         d.half_width = base_width * attr(ep) * 0.5f;  // stroke.rs:689
                         step(d);
@@ -546,6 +549,7 @@ public:
                     current_position = to;
                     cur_ep = ep;
                     uint32_t to_id = with_ids ? ep : seq_id;
+                    uint32_t from_id = with_ids ? from_ep : seq_id - 1u;  // the previous event's id (stroke.rs:905-923)
                     float start_width = 0.0f, end_width = 0.0f;
                     if (vw) {
                         start_width = base_width * attr(from_ep);  // stroke.rs:705-706
@@ -556,7 +560,7 @@ public:
                         EndpointData d = endpoint_default();
                         d.position = p;
                         d.line_join = options.line_join;
-                        d.src = Source{to_id, t};  // t == 1.0 -> Endpoint (stroke.rs:1009-1017)
+                        d.src = Source{to_id, t, from_id};  // t == 1.0 -> Endpoint (stroke.rs:1009-1017)
                         d.is_flattening_step = fs;
                         if (vw) {
                             d.half_width = (start_width * (1.0f - t) + end_width * t) * 0.5f;  // :1022
@@ -580,6 +584,7 @@ public:
                     current_position = to;
                     cur_ep = ep;
                     uint32_t to_id = with_ids ? ep : seq_id;
+                    uint32_t from_id = with_ids ? from_ep : seq_id - 1u;  // the previous event's id (stroke.rs:905-923)
                     float start_width = 0.0f, end_width = 0.0f;
                     if (vw) {
                         start_width = base_width * attr(from_ep);  // stroke.rs:731-732
@@ -591,7 +596,7 @@ public:
                         EndpointData d = endpoint_default();
                         d.position = p;
                         d.line_join = options.line_join;
-                        d.src = Source{to_id, t};
+                        d.src = Source{to_id, t, from_id};
                         d.is_flattening_step = fs;
                         if (vw) {
                             d.half_width = (start_width * (1.0f - t) + end_width * t) * 0.5f;  // :1058
@@ -649,7 +654,9 @@ private:
         v.half_width = vertex.half_width;
         v.src = (vertex.src.id & 0x7FFFFFFFu) | (vertex.side_negative ? SIDE_NEG_BIT : 0u);
         v.t = vertex.src.t;
-        return output.add_vertex(v, id);
+        if (!output.add_vertex(v, id)) return false;
+        output.vertex_from.push_back(vertex.src.from);
+        return true;
     }
     bool points_are_too_close(V2 p0, V2 p1) const {  // stroke.rs:1318-1320
         return sqlen(p0 - p1) < square_merge_threshold;

@@ -57,6 +57,29 @@ void oracle_mesh_copy(const oracle_mesh* m, void* vertices, uint32_t* indices, u
 }
 void oracle_mesh_free(oracle_mesh* m) { delete m; }
 
+// StrokeVertex::interpolated_attributes (stroke.rs:2728-2747) of every vertex of the mesh, against the paths' own
+// attribute stores (Path as AttributeStore: the f32s stored after the endpoint, path.rs:650-665):
+// Endpoint{id} -> store.get(id); Edge{from, to, t} -> a[i] * (1.0 - t) + b[i] * t.  out[v * num_attributes + i].
+void oracle_mesh_interpolated_attributes(const oracle_mesh* m, const float* points, const uint32_t* path_point_begin,
+                                         uint32_t num_attributes, float* out) {
+    size_t v = 0;
+    for (size_t p = 0; p < m->path_vertex_end.size(); ++p) {
+        const float* store = points + 2 * (size_t)path_point_begin[p];
+        for (; v < m->path_vertex_end[p]; ++v) {
+            const Vertex& vx = m->buf.vertices[v];
+            const float* b = store + 2 * ((size_t)(vx.src & 0x7FFFFFFFu) + 1);
+            float* o = out + v * num_attributes;
+            if (vx.t == 1.0f) {
+                for (uint32_t i = 0; i < num_attributes; ++i) o[i] = b[i];
+            } else {
+                const float* a = store + 2 * ((size_t)m->buf.vertex_from[v] + 1);
+                const float t = vx.t;
+                for (uint32_t i = 0; i < num_attributes; ++i) o[i] = a[i] * (1.0f - t) + b[i] * t;
+            }
+        }
+    }
+}
+
 // Timed multi-threaded run for the CPU baseline ("rayon-parallel over paths" stand-in): the batch is cut
 // into n_threads contiguous ranges of equal verb count; every worker tessellates its range into its own
 // VertexBuffers.  Like bench/tess (which reuses a pre-sized VertexBuffers across iterations) the buffers are

@@ -94,6 +94,9 @@ extern "C" {
                                         d_out_path_verb_begin: *mut u32, d_out_path_point_begin: *mut u32) -> c_int;
     pub fn lyon_cuda_rebase_indices(ctx: *mut lyon_cuda_ctx, d_indices: *mut u32, n_indices: u64, n_vertices: u64,
                                     vertex_base: u64) -> c_int;
+    pub fn lyon_cuda_interpolate_attributes(ctx: *mut lyon_cuda_ctx, d_batch: *const lyon_path_batch,
+                                            d_vertices: *const lyon_stroke_vertex, n_vertices: u64,
+                                            d_path_vertex_end: *const u64, d_out: *mut f32) -> c_int;
     pub fn lyon_cuda_set_pipeline(ctx: *mut lyon_cuda_ctx, pipeline: c_int) -> c_int;
     pub fn lyon_cuda_enable_timing(ctx: *mut lyon_cuda_ctx, on: c_int) -> c_int;
     pub fn lyon_cuda_last_kernel_ms(ctx: *mut lyon_cuda_ctx, ms: *mut f32) -> c_int;

@@ -36,6 +36,7 @@ def lib():
         L.oracle_mesh_num_indices.argtypes = [ctypes.c_void_p]
         L.oracle_mesh_copy.argtypes = [ctypes.c_void_p] * 5
         L.oracle_mesh_free.argtypes = [ctypes.c_void_p]
+        L.oracle_mesh_interpolated_attributes.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint32, ctypes.c_void_p]
         L.oracle_stroke_batch_timed.restype = ctypes.c_double
         L.oracle_stroke_batch_timed.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_uint32,
                                                                         ctypes.POINTER(CStrokeOptions), ctypes.c_int,
@@ -77,7 +78,8 @@ class OracleError(Exception):
         self.code = code
 
 
-def stroke_batch(batch: PathBatch, opts: StrokeOptions, max_index: int = 0xFFFFFFFE, with_ranges=False):
+def stroke_batch(batch: PathBatch, opts: StrokeOptions, max_index: int = 0xFFFFFFFE, with_ranges=False,
+                 with_attributes=False):
     L = lib()
     c = opts.to_c()
     err = ctypes.c_int(0)
@@ -96,8 +98,13 @@ def stroke_batch(batch: PathBatch, opts: StrokeOptions, max_index: int = 0xFFFFF
         pve = np.zeros(batch.n_paths, np.uint64)
         pie = np.zeros(batch.n_paths, np.uint64)
         L.oracle_mesh_copy(m, _p(v), _p(i), _p(pve), _p(pie))
+        if with_attributes:  # StrokeVertex::interpolated_attributes of every vertex, [V, num_attributes]
+            attrs = np.zeros((nv, batch.num_attributes), np.float32)
+            L.oracle_mesh_interpolated_attributes(m, _p(pts), _p(pb), batch.num_attributes, _p(attrs))
     finally:
         L.oracle_mesh_free(m)
+    if with_attributes:
+        return (VertexBuffers(v, i), pve, pie, attrs) if with_ranges else (VertexBuffers(v, i), attrs)
     if with_ranges:
         return VertexBuffers(v, i), pve, pie
     return VertexBuffers(v, i)

@@ -191,6 +191,48 @@ def test_variable_width_adversarial_paths(tz, num_attributes, attr):
                                    what=str(o))
 
 
+@pytest.mark.parametrize("num_attributes", [1, 2, 3])
+def test_interpolated_attributes(tz, num_attributes):
+    """StrokeVertex::interpolated_attributes (stroke.rs:2728-2747) on the device against the oracle, bit for bit: endpoint
+    vertices copy their endpoint's attributes, curve vertices lerp between the curve's endpoints with the vertex's t."""
+    import torch
+    if ROUTE != "tile":
+        pytest.skip("one route")
+    batch = W.random_width_paths(300, seed=90 + num_attributes, num_attributes=num_attributes)
+    for o in (StrokeOptions(tolerance=0.05, line_width=1.5).with_variable_line_width(0),
+              StrokeOptions(tolerance=0.1, line_width=2.0, line_join=LineJoin.Round).with_line_cap(LineCap.Round)):
+        d = tz.upload(batch)
+        v, i, pve, pie = tz.stroke(d, o, with_ranges=True)
+        got = tz.interpolate_attributes(d, v, pve)
+        torch.cuda.synchronize()
+        tz.check()
+        want_mesh, want = O.stroke_batch(batch, o, with_attributes=True)
+        assert got.shape == want.shape and want.shape[0] == v.shape[0]
+        edge = want_mesh.vertices["t"] != 1.0
+        assert edge.any() and (~edge).any()
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32)), str(o)
+
+
+def test_interpolated_attributes_reference_case(tz):
+    """stroke_vertex_source_01 (stroke.rs:3040-3124) through the device path."""
+    import torch
+    from lyon_b200 import Path, PathBatch
+    b = Path.builder_with_attributes(1)
+    b.begin((0.0, 0.0), [1.0]); b.line_to((10.0, 10.0), [2.0])
+    b.quadratic_bezier_to((10.0, 20.0), (0.0, 20.0), [3.0]); b.end(True)
+    batch = PathBatch.from_paths([b.build()])
+    d = tz.upload(batch)
+    v, i, pve, pie = tz.stroke(d, StrokeOptions().with_variable_line_width(0), with_ranges=True)
+    a = tz.interpolate_attributes(d, v, pve).cpu().numpy()
+    pos = v.cpu().numpy()[:, 0:2]
+    for k in range(len(pos)):
+        def eq(q): return abs(pos[k][0] - q[0]) < 1e-5 and abs(pos[k][1] - q[1]) < 1e-5
+        if eq((0, 0)): assert a[k, 0] == 1.0
+        elif eq((10, 10)): assert a[k, 0] == 2.0
+        elif eq((0, 20)): assert a[k, 0] == 3.0
+        else: assert 2.0 < a[k, 0] < 3.0
+
+
 @pytest.mark.parametrize("tol", [1.0, 0.3, 0.1, 0.03, 0.01, 0.003, 0.001])
 def test_c5_tolerance_sweep(tz, tol):
     batch = W.c5_logo_copies(W.fixture_paths(GOLDEN), 40)

@@ -168,6 +168,16 @@ def test_stroke_vertex_source_01():  # stroke.rs:3040-3124
             # interpolated line width (attribute 1 -> lerp between 2 and 3): stroke.rs:1022
             w = float(v["half_width"][i]) * 2.0
             assert 2.0 < w < 3.0
+    # attr.interpolated_attributes() of every vertex (stroke.rs:3105-3117)
+    vb2, attrs = O.stroke_batch(PathBatch.from_paths([path]), StrokeOptions().with_variable_line_width(0), with_attributes=True)
+    assert attrs.shape == (len(v), 1)
+    for i in range(len(v)):
+        pos = v["position_on_path"][i]
+        def eq(q): return abs(pos[0] - q[0]) < 1e-5 and abs(pos[1] - q[1]) < 1e-5
+        if eq((0, 0)): assert attrs[i, 0] == 1.0
+        elif eq((10, 10)): assert attrs[i, 0] == 2.0
+        elif eq((0, 20)): assert attrs[i, 0] == 3.0
+        else: assert 2.0 < attrs[i, 0] < 3.0
 
 
 def test_compute_normal():  # math_utils.rs:42-62
