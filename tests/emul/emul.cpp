@@ -176,7 +176,7 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         uint32_t vb = b->path_verb_begin[verb_path[v]];
         uint32_t id = p.num_attributes > 0 ? (seg_pt[v] - seg_pt[vb]) + ncurve - 1u : evt_before[v] - evt_before[vb];
         if (verb == VERB_QUAD && plans[v].tsplit >= 0.0f) {  // the tile kernel's warp-per-split-quadratic route
-            for (uint32_t lane = 0; lane < 32u; ++lane) tile_gen_split_quad(w, p, points, seg_pt[v], seg_off[v], id, lane, 32u);
+            for (uint32_t lane = 0; lane < 8u; ++lane) tile_gen_split_quad(w, p, points, seg_pt[v], seg_off[v], id, lane, 8u);
             continue;
         }
         tile_gen_verb(w, p, verb, points, seg_pt[v], plans[v], seg_off[v], id);
