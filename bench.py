@@ -284,7 +284,7 @@ def main():
         "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: ncu --set full on the first 200k paths of the same
         # batch measured 9.647 GB for 8.686 GB of algorithmic bytes (profiles/r01k_ncu_summary.txt); scaled to this launch
-        "traffic": int(alg_bytes * (9.315 / 8.686)), "traffic_source": "ncu capture on a 200k-path sample, scaled by algorithmic bytes",
+        "traffic": int(alg_bytes * (9.362 / 8.686)), "traffic_source": "ncu capture on a 200k-path sample, scaled by algorithmic bytes",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms": dev_ms / args.steps,
         "kernel_share_of_step": k_ms / (dev_ms / args.steps),
         "whole_step_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
