@@ -109,37 +109,30 @@ template <class Sink>
 struct VwStroker {
     const StrokeParams& o;
     Sink& sink;
-    VwPoint pts[3];  // PointBuffer (stroke.rs:2371-2457)
-    int start, count;
+    // PointBuffer (stroke.rs:2371-2457) keeps the last three points in a ring, but only the last two are ever read
+    // (`prev` and `join` of a step, the two ends of the last edge); two named points stay in registers where a ring
+    // indexed by (idx + start) % 3 lives in local memory.  `count` saturates at 3 like the reference's.
+    VwPoint p_mid, p_new;
+    int count;
     VwPoint firsts[2];
     int n_firsts;
     float sub_path_start_advancement;
     bool may_need_empty_cap;
 
     LYC_HD VwStroker(const StrokeParams& o_, Sink& s_) : o(o_), sink(s_) {
-        start = count = 0;
+        count = 0;
         n_firsts = 0;
         sub_path_start_advancement = 0.0f;
         may_need_empty_cap = false;
     }
-    LYC_HD VwPoint& get(int idx) { return pts[(idx + start) % 3]; }
-    LYC_HD VwPoint& last() { return get(count - 1); }
-    LYC_HD VwPoint& last_but_one() { return pts[(start + count - 2) % 3]; }
+    LYC_HD VwPoint& last() { return p_new; }
+    LYC_HD VwPoint& last_but_one() { return p_mid; }
     LYC_HD void push(const VwPoint& p) {
-        if (count < 3) {
-            pts[count] = p;
-            count += 1;
-            return;
-        }
-        pts[start] = p;
-        start += 1;
-        if (start == 3) start = 0;
+        p_mid = p_new;
+        p_new = p;
+        if (count < 3) count += 1;
     }
-    LYC_HD void replace_last(const VwPoint& p) {
-        int idx = start;
-        if (idx == 0) idx = count;
-        pts[idx - 1] = p;
-    }
+    LYC_HD void replace_last(const VwPoint& p) { p_new = p; }
 
     // flattened_step (stroke.rs:1743-1806); returns the skip flag
     LYC_HD bool flattened_step(VwPoint& prev, VwPoint& join, VwPoint& next) {
@@ -239,7 +232,7 @@ struct VwStroker {
     // end_with_caps (stroke.rs:1322-1378)
     LYC_HD void end_with_caps() {
         if (may_need_empty_cap && count == 1) {
-            tessellate_empty_cap(sink, vw_vertex(get(0)), o);
+            tessellate_empty_cap(sink, vw_vertex(last()), o);  // count == 1
             return;
         }
         if (count >= 2) {
@@ -281,7 +274,7 @@ struct VwStroker {
             close_subpath();
         else
             end_with_caps();
-        count = start = 0;
+        count = 0;
         n_firsts = 0;
     }
 };
