@@ -946,7 +946,10 @@ __global__ void __launch_bounds__(256) k_rebase_indices(uint32_t* __restrict__ i
 // ---------------------------------------------------------------------------------------------------------
 // Variable line width (stroke_vw.cuh): one thread per path runs the streaming state machine, once to count, once to emit.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vw_count(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+#ifndef LYON_VW_MINB
+#define LYON_VW_MINB 3  // resident 128-thread blocks per SM the variable-width kernels are compiled for (168 registers; C4: 28.6 ms uncapped, 22.2 ms at 3, 27.0 ms at 4)
+#endif
+__global__ void __launch_bounds__(128, LYON_VW_MINB) k_vw_count(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
                                                   const uint32_t* __restrict__ path_verb_begin,
                                                   const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, StrokeParams p,
                                                   uint32_t* __restrict__ path_nv, uint32_t* __restrict__ path_nt) {
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(BLOCK) k_scan_counts(const uint32_t* __restric
         if (i0 + k + 1 == n) out[n] = run;
     }
 }
-__global__ void __launch_bounds__(128) k_vw_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+__global__ void __launch_bounds__(128, LYON_VW_MINB) k_vw_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
                                                  const uint32_t* __restrict__ path_verb_begin,
                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, StrokeParams p,
                                                  const unsigned long long* __restrict__ path_v0,
