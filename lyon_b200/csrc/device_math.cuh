@@ -203,21 +203,30 @@ LYC_HD bool quad_local_x_extremum_t(V2 from, V2 ctrl, V2 to, float* t_out) {
     return false;
 }
 // crates/tessellation/src/stroke.rs:3178-3212
-LYC_HD bool find_sharp_turn(V2 from, V2 ctrl, V2 to, float* t_out) {
+// find_sharp_turn (stroke.rs:3178-3212) in two steps: the cheap test that sends most quadratics away (false), and the
+// search itself (rotation onto the long axis, local x extremum) for the candidates it leaves.
+LYC_HD bool sharp_turn_candidate(V2 from, V2 ctrl, V2 to, V2* long_axis) {
     V2 baseline = to - from;
     V2 v = ctrl - from;
     V2 n = v2(-baseline.y, baseline.x);
     float v_dot_b = dot(v, baseline);
     float v_dot_n = dot(v, n);
-    V2 long_axis;
     if ((v_dot_b >= 0.0f && v_dot_b <= dot(baseline, baseline)) || fabsf(v_dot_n) * 2.0f >= fabsf(v_dot_b)) {
         if (sqlen(baseline) * 30.0f > sqlen(v)) return false;
-        long_axis = v;
+        *long_axis = v;
     } else {
-        long_axis = baseline;
+        *long_axis = baseline;
     }
+    return true;
+}
+LYC_HD bool find_sharp_turn(V2 from, V2 ctrl, V2 to, float* t_out) {
+    V2 long_axis;
+    if (!sharp_turn_candidate(from, ctrl, to, &long_axis)) return false;
+    V2 baseline = to - from;
+    V2 v = ctrl - from;
     float ang = -angle_from_x_axis(long_axis);
-    float s = libm_sin(ang), c = libm_cos(ang);
+    const V2 cs = libm_cos_sin(ang);  // one double-precision sincos: the same two values as cos() and sin()
+    float s = cs.y, c = cs.x;
     V2 rctrl = v2(v.x * c - v.y * s, v.y * c + v.x * s);
     V2 rto = v2(baseline.x * c - baseline.y * s, baseline.y * c + baseline.x * s);
     return quad_local_x_extremum_t(v2(0.0f, 0.0f), rctrl, rto, t_out);
