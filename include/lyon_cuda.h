@@ -49,7 +49,9 @@ typedef struct {
     float tolerance;
 } lyon_stroke_options;
 
-/* StrokeVertexGpu: everything lyon's StrokeVertex exposes (stroke.rs:2656-2747), 32 bytes, 16-byte aligned.
+/* StrokeVertexGpu: everything lyon's StrokeVertex exposes (stroke.rs:2656-2747), 32 bytes.  DEVICE vertex arrays
+ * handed to lyon_cuda_stroke_emit / lyon_cuda_stroke_fused must be 32-byte aligned (every cudaMalloc'ed pointer is):
+ * the kernels write a vertex with one 256-bit store; a misaligned array is rejected with LYON_ERR_INVALID_ARGUMENT.
  *   position()  = position_on_path + normal * half_width      (stroke.rs:2676-2678)
  *   side        = (src & 0x80000000) ? Side::Negative : Side::Positive
  *   source      = t == 1.0 ? VertexSource::Endpoint{ id: src & 0x7fffffff }

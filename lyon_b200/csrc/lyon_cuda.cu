@@ -22,6 +22,7 @@
 
 #include "../../include/lyon_cuda.h"
 #include "stroke_tile.cuh"
+#include "stroke_wtile.cuh"
 #include "stroke_vw.cuh"
 
 using namespace lyc;
@@ -1028,6 +1029,7 @@ __global__ void __launch_bounds__(128, LYON_VW_MINB) k_vw_emit(const uint8_t* __
 }
 
 #include "tile_kernels.cuh"
+#include "wtile_kernels.cuh"
 
 }  // namespace
 
@@ -1052,6 +1054,14 @@ struct lyon_cuda_ctx {
     Totals* h_totals = nullptr;  // pinned
     // fused tile pipeline
     DevBuf verb_n, path_slots, path_events, path_slot_begin, path_event_begin, tile_first, tile_desc, tile_base, tile_misc;
+    // warp-tile pipeline (wtile_kernels.cuh)
+    DevBuf split_rec, path_split_begin, end_rec;
+    uint32_t split_cap = 0, end_rec_cap = 0;
+    bool tile_is_wtile = false;   // the tile table of the last pre-pass is for k_stroke_wtile
+    bool tile_has_split_recs = false;  // the pre-pass kept the plan of every split quadratic
+    int wt_warps = 0;             // warps per CTA (= tiles in flight per SM)
+    uint32_t wt_s_cap = 0, wt_v_cap = 0, wt_p_cap = 0, wt_bytes = 0;
+    int wt_mode = 0;              // 1 (LYON_PIPE=wtile / set_pipeline 3): warp tiles whenever they fit; 0: CTA tiles
     TileTotals* h_tile_totals = nullptr;  // pinned
     bool tile_planned = false;            // the last plan went through the tile pipeline
     bool vw_planned = false;              // the last plan went through the variable-width (thread per path) kernels
@@ -1275,9 +1285,62 @@ bool tile_config(const lyon_cuda_ctx* c, uint32_t max_path, unsigned long long t
     return true;
 }
 
-// Pre-pass: per-path slot counts, their scan, the tile table.  *usable = the batch fits the tile pipeline.
-int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
+// Warp-tile geometry: the largest number of warps per SM (16 .. 6) whose share of the shared memory holds the longest
+// path of the batch, with the rest of the share given to slots (several short paths per tile) at the batch's average
+// verbs-per-slot and points-per-slot ratios.  LYON_WT=warps,s_cap,v_cap,p_cap overrides.
+bool wtile_config(lyon_cuda_ctx* c, const lyon_path_batch* b, const TileTotals& t) {
+    if (c->wt_mode != 1) return false;  // experiment, measured 3x slower than CTA tiles on C3 (profiles/r02_experiments.md)
+    if (t.wt_flags & WT_FLAG_NO_SPLIT_RECS) return false;
+    const uint32_t back = 1u + (b->num_attributes + 1u) / 2u;
+    const uint32_t need_s = t.max_path_slots ? t.max_path_slots : 1u, need_v = t.max_path_verbs ? t.max_path_verbs : 1u;
+    const uint32_t need_p = t.max_path_points + back + 2u;
+    if (need_s > 60000u || need_p > 60000u) return false;
+    if (const char* e = getenv("LYON_WT")) {
+        unsigned wq = 0, sc = 0, vc = 0, pc = 0;
+        if (sscanf(e, "%u,%u,%u,%u", &wq, &sc, &vc, &pc) == 4 && wq >= 1 && wq <= 16 && sc >= need_s && vc >= need_v && pc >= need_p &&
+            sc <= 60000u && pc <= 60000u) {
+            const WtLayout L = wt_layout(sc, vc, pc);
+            if ((size_t)L.total * wq <= c->max_smem_optin) {
+                c->wt_warps = (int)wq;
+                c->wt_s_cap = sc;
+                c->wt_v_cap = vc;
+                c->wt_p_cap = pc;
+                c->wt_bytes = L.total;
+                return true;
+            }
+        }
+    }
+    const double total = t.total_slots ? (double)t.total_slots : 1.0;
+    const double rv = (double)b->n_verbs / total, rp = (double)b->n_points / total;
+    for (int wq = 16; wq >= 6; --wq) {
+        const uint32_t budget = (uint32_t)(c->max_smem_optin / (size_t)wq) & ~127u;
+        uint32_t sc = (budget / 20u) & ~31u;
+        if (sc > 60000u) sc = 60000u & ~31u;
+        for (; sc >= need_s && sc >= 64u; sc -= 32u) {
+            uint32_t vc = (uint32_t)((double)sc * rv) + 8u, pc = (uint32_t)((double)sc * rp) + back + 8u;
+            if (vc > sc) vc = sc;
+            if (vc < need_v) vc = need_v;
+            if (pc < need_p) pc = need_p;
+            if (pc > 60000u) continue;
+            const WtLayout L = wt_layout(sc, vc, pc);
+            if (L.total <= budget) {
+                c->wt_warps = wq;
+                c->wt_s_cap = sc;
+                c->wt_v_cap = vc;
+                c->wt_p_cap = pc;
+                c->wt_bytes = L.total;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// Pre-pass: per-path slot counts, their scan, the tile table.  *usable = the batch fits a tile pipeline; which one is
+// left in c->tile_is_wtile (warp tiles when `allow_wtile` and the longest path fits a warp's share of shared memory).
+int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable, bool allow_wtile = true) {
     *usable = false;
+    c->tile_is_wtile = false;
     if (c->tile_force_general || !b->path_point_begin || b->n_paths == 0 || b->n_verbs == 0) return LYON_OK;
     const uint32_t np = b->n_paths;
     TRY(ensure(c, c->verb_n, ((size_t)b->n_verbs + 1) * 4));
@@ -1285,6 +1348,11 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     TRY(ensure(c, c->path_events, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->path_slot_begin, ((size_t)np + 1) * 8));
     TRY(ensure(c, c->path_event_begin, ((size_t)np + 1) * 4));
+    TRY(ensure(c, c->path_split_begin, ((size_t)np + 1) * 4));
+    // plans of the split quadratics: one verb in eight is plenty (C3: one in thirty); more => CTA-tile pipeline
+    const size_t split_cap = (size_t)b->n_verbs / 8u + 1024u;
+    TRY(ensure(c, c->split_rec, split_cap * sizeof(SplitRec)));
+    c->split_cap = (uint32_t)(split_cap > 0x7FFFFFFFull ? 0x7FFFFFFFull : split_cap);
     TRY(ensure(c, c->tile_misc, 512));
     const unsigned ptiles = grid_for(np, BLOCK * PSCAN_ITEMS);
     TRY(ensure(c, c->tile_desc, (size_t)ptiles * 16));
@@ -1295,7 +1363,8 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
     k_path_slots<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
                                                b->path_point_begin, np, c->params, (uint32_t*)c->path_slots.p,
-                                               (uint32_t*)c->path_events.p, (float*)c->verb_n.p, d_tile_totals(c));
+                                               (uint32_t*)c->path_events.p, (float*)c->verb_n.p, (SplitRec*)c->split_rec.p,
+                                               c->split_cap, (uint32_t*)c->path_split_begin.p, d_tile_totals(c));
     k_scan_paths<<<ptiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->path_slots.p, (const uint32_t*)c->path_events.p, np,
                                                  (unsigned long long*)c->path_slot_begin.p, (uint32_t*)c->path_event_begin.p,
                                                  d_tile_ticket(c, 0), (uint64_t*)c->tile_desc.p,
@@ -1308,24 +1377,45 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
         return LYON_ERR_INVALID_ARGUMENT;
     }
     const unsigned long long total = c->h_tile_totals->total_slots;
-    TileGeom g;
-    uint32_t q;
-    if (!tile_config(c, c->h_tile_totals->max_path_slots, total, &g, &q)) return LYON_OK;
-    const uint32_t s_cap = g.s_cap, w_v = g.w_v, w_t = g.w_t;
-    c->tile_nt = g.nt;
-    // tile table: greedy packing inside coarse blocks (k_tile_pack), two passes around a scan of the per-block counts
     const uint32_t max_path = c->h_tile_totals->max_path_slots ? c->h_tile_totals->max_path_slots : 1u;
-    uint32_t cap = q + max_path - 1u;  // what a tile of the quantum `q` could hold at most (q shrinks for small batches)
-    if (cap > s_cap) cap = s_cap;
+    uint32_t s_cap = 0, cap = 0, group = 0, v_cap = 0, p_cap = 0;
+    c->tile_has_split_recs = !(c->h_tile_totals->wt_flags & WT_FLAG_NO_SPLIT_RECS);
+    {
+        const unsigned long long n_ends = (unsigned long long)b->n_verbs - c->h_tile_totals->total_events;
+        TRY(ensure(c, c->end_rec, (size_t)(n_ends + 1ull) * sizeof(EndRecord)));
+        c->end_rec_cap = (uint32_t)(n_ends > 0xFFFFFFFEull ? 0xFFFFFFFEull : n_ends);
+    }
+    if (allow_wtile && wtile_config(c, b, *c->h_tile_totals)) {
+        c->tile_is_wtile = true;
+        s_cap = cap = c->wt_s_cap;
+        // small batches: shrink the tiles so that every warp of every SM still gets a few
+        const unsigned long long spread = total / (4ull * (unsigned long long)c->num_sms * (unsigned long long)c->wt_warps) + 1ull;
+        if (spread < cap) cap = (uint32_t)(spread < max_path ? max_path : spread);
+        v_cap = c->wt_v_cap;
+        p_cap = c->wt_p_cap - (1u + (b->num_attributes + 1u) / 2u) - 2u;
+        c->tile_w_v = c->tile_w_t = c->tile_quantum = 0;
+    } else {
+        TileGeom g;
+        uint32_t q;
+        if (!tile_config(c, c->h_tile_totals->max_path_slots, total, &g, &q)) return LYON_OK;
+        s_cap = g.s_cap;
+        c->tile_nt = g.nt;
+        c->tile_w_v = g.w_v;
+        c->tile_w_t = g.w_t;
+        c->tile_quantum = q;
+        cap = q + max_path - 1u;  // what a tile of the quantum `q` could hold at most (q shrinks for small batches)
+        if (cap > s_cap) cap = s_cap;
+#ifdef LYON_DEV_BUILD
+        group = (uint32_t)LYON_DEV_NT_OR_DEFAULT / 32u;
+#else
+        group = (uint32_t)(g.nt & ~31) / 32u;
+#endif
+        if (const char* e = getenv("LYON_TILE_GROUP")) group = (uint32_t)atoi(e);  // experiments: 0 switches the trimming off
+    }
+    // tile table: greedy packing inside coarse blocks (k_tile_pack), two passes around a scan of the per-block counts.
     // coarse block = what one thread packs: 32 tiles' worth of slots, fewer for small batches (the packing of a block is
     // sequential, and a batch of a few hundred tiles should still spread over many threads)
     unsigned long long qc = 32ull * cap;
-#ifdef LYON_DEV_BUILD
-    uint32_t group = (uint32_t)LYON_DEV_NT_OR_DEFAULT / 32u;
-#else
-    uint32_t group = (uint32_t)(g.nt & ~31) / 32u;
-#endif
-    if (const char* e = getenv("LYON_TILE_GROUP")) group = (uint32_t)atoi(e);  // experiments: 0 switches the trimming off
     if (total / 512ull < qc) qc = total / 512ull;
     if (qc < 2ull * cap) qc = 2ull * cap;
     const unsigned long long n_blocks64 = total / qc + 1ull;
@@ -1339,7 +1429,8 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)btiles * 8, c->stream));
     k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, group, n_blocks,
-                                                               (uint32_t*)c->vw_nv.p, nullptr, nullptr);
+                                                               (uint32_t*)c->vw_nv.p, nullptr, nullptr, b->path_verb_begin,
+                                                               b->path_point_begin, v_cap, p_cap);
     k_scan_counts<<<btiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, n_blocks, (unsigned long long*)c->vw_v0.p,
                                                   d_ticket(c, 0), (uint64_t*)c->desc.p);
     unsigned long long n_tiles64 = 0ull;
@@ -1349,18 +1440,29 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable) {
     if (n_tiles64 == 0ull || n_tiles64 > 0x7FFFFFFFull) return LYON_OK;
     c->tile_n_tiles = (uint32_t)n_tiles64;
     c->tile_s_cap = s_cap;
-    c->tile_w_v = w_v;
-    c->tile_w_t = w_t;
-    c->tile_quantum = q;
     TRY(ensure(c, c->tile_first, ((size_t)c->tile_n_tiles + 1) * 4));
     TRY(ensure(c, c->tile_desc, (size_t)c->tile_n_tiles * 16));
     TRY(ensure(c, c->tile_base, (size_t)c->tile_n_tiles * 16));
     k_tile_pack<<<grid_for(n_blocks, 128), 128, 0, c->stream>>>((const unsigned long long*)c->path_slot_begin.p, np, qc, cap, group, n_blocks,
-                                                               nullptr, (const unsigned long long*)c->vw_v0.p, (uint32_t*)c->tile_first.p);
+                                                               nullptr, (const unsigned long long*)c->vw_v0.p, (uint32_t*)c->tile_first.p,
+                                                               b->path_verb_begin, b->path_point_begin, v_cap, p_cap);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     c->tile_batch = *b;
+    c->vw_planned = false;  // the pre-pass reuses the variable-width / path-flattening count buffers
+    c->pf_planned = false;
     *usable = true;
+    return LYON_OK;
+}
+
+// Everything end() emits: the EndRecords the tile kernel left behind, one thread each.
+int ends_launch(lyon_cuda_ctx* c, const TileArgs& a) {
+    if (!c->end_rec_cap) return LYON_OK;
+    unsigned eb = (c->end_rec_cap + 127u) / 128u;
+    if (eb > (unsigned)c->num_sms * 16u) eb = (unsigned)c->num_sms * 16u;
+    k_stroke_ends<<<eb, 128, 0, c->stream>>>(a.end_rec, a.n_end_rec, a.end_rec_cap, c->params, a.vertices, a.indices, a.totals);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
     return LYON_OK;
 }
 
@@ -1378,14 +1480,45 @@ int tile_launch_nt(lyon_cuda_ctx* c, const TileArgs& a) {
     unsigned grid = (unsigned)c->num_sms * (unsigned)per_sm;
     if (grid > a.n_tiles) grid = a.n_tiles;
     CU_TRY(c, cudaMemsetAsync(a.ticket, 0, 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(a.n_end_rec, 0, 4, c->stream));
     if (MODE != TILE_MODE_EMIT) CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)c->tile_n_tiles * 16, c->stream));
     if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
     kern<<<grid, NT, smem, c->stream>>>(a, c->params);
+    if (MODE != TILE_MODE_COUNT) TRY(ends_launch(c, a));
     if (c->timing) {
         CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
         c->ev_valid = true;
     }
     c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
+
+// Warp-tile launch: one CTA of wt_warps warps per SM, every warp a tile of its own; then the End records.
+template <int MODE>
+int wtile_launch(lyon_cuda_ctx* c, const TileArgs& a) {
+    WtArgs x{};
+    x.s_cap = c->wt_s_cap;
+    x.v_cap = c->wt_v_cap;
+    x.p_cap = c->wt_p_cap;
+    x.warp_bytes = c->wt_bytes;
+    const size_t smem = (size_t)c->wt_bytes * (size_t)c->wt_warps;
+    auto kern = k_stroke_wtile<MODE>;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)c->num_sms;
+    const unsigned want = (a.n_tiles + (unsigned)c->wt_warps - 1u) / (unsigned)c->wt_warps;
+    if (grid > want) grid = want;
+    CU_TRY(c, cudaMemsetAsync(a.ticket, 0, 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(a.n_end_rec, 0, 4, c->stream));
+    if (MODE != TILE_MODE_EMIT) CU_TRY(c, cudaMemsetAsync(c->tile_desc.p, 0, (size_t)c->tile_n_tiles * 16, c->stream));
+    if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    kern<<<grid, c->wt_warps * 32, smem, c->stream>>>(a, x, c->params);
+    c->launches++;
+    if (MODE != TILE_MODE_COUNT) TRY(ends_launch(c, a));
+    if (c->timing) {
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+    }
     CU_TRY(c, cudaGetLastError());
     return LYON_OK;
 }
@@ -1421,6 +1554,12 @@ int tile_launch(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, ui
     a.totals = d_tile_totals(c);
     a.path_vertex_end = (unsigned long long*)d_path_vertex_end;
     a.path_index_end = (unsigned long long*)d_path_index_end;
+    a.path_split_begin = c->tile_has_split_recs ? (const uint32_t*)c->path_split_begin.p : nullptr;
+    a.split_rec = c->tile_has_split_recs ? (const SplitRec*)c->split_rec.p : nullptr;
+    a.end_rec = (EndRecord*)c->end_rec.p;
+    a.n_end_rec = &d_tile_totals(c)->n_end_rec;
+    a.end_rec_cap = c->end_rec_cap;
+    if (c->tile_is_wtile) return wtile_launch<MODE>(c, a);
 #ifdef LYON_DEV_BUILD  // experiments only: one instantiation, compiles 4x faster
 #ifndef LYON_DEV_NT
 #define LYON_DEV_NT 256
@@ -1531,6 +1670,7 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return LYON_ERR_CUDA;
     lyon_cuda_ctx* c = new lyon_cuda_ctx();
     c->device = device;
+    if (const char* e = getenv("LYON_PIPE")) c->wt_mode = strcmp(e, "wtile") == 0 ? 1 : 0;  // experiments: warp tiles
     c->stream = (cudaStream_t)stream;  // NULL is CUDA's default stream
     {
         cudaDeviceProp prop;
@@ -1718,6 +1858,16 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
         if (usable) {
             TRY((tile_launch<TILE_MODE_COUNT>(c, nullptr, nullptr, 0, 0, 0, nullptr, nullptr)));
             TRY(fetch_tile_totals(c));
+            if (c->tile_is_wtile && (c->h_tile_totals->error & TILE_ERR_WT_OVERFLOW)) {
+                // a join or cap with more than 65535 vertices: warp tiles keep 16-bit offsets, CTA tiles do not
+                TRY(tile_prepass(c, b, &usable, false));
+                if (usable) {
+                    TRY((tile_launch<TILE_MODE_COUNT>(c, nullptr, nullptr, 0, 0, 0, nullptr, nullptr)));
+                    TRY(fetch_tile_totals(c));
+                }
+            }
+        }
+        if (usable) {
             TRY(tile_error(c));
             c->n_vertices = c->h_tile_totals->vertices;
             c->n_triangles = c->h_tile_totals->triangles;
@@ -1812,6 +1962,10 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
     }
     // ids handed out are vertex_base .. vertex_base + V - 1 and must be <= u32::MAX - 1 (geometry_builder.rs:342-346)
     if (c->n_vertices && vertex_base + c->n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    if (reinterpret_cast<uintptr_t>(d_vertices) & 31u) {
+        c->err = "d_vertices must be 32-byte aligned (vertices leave the SM as 256-bit stores)";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
     if (c->vw_planned) return vw_emit(c, (GpuVertex*)d_vertices, d_indices, vertex_base, d_path_vertex_end, d_path_index_end);
     if (c->tile_planned) {
         if ((c->n_vertices && !d_vertices) || (c->n_triangles && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
@@ -1924,8 +2078,11 @@ int lyon_cuda_interpolate_attributes(lyon_cuda_ctx* c, const lyon_path_batch* b,
 }
 
 int lyon_cuda_set_pipeline(lyon_cuda_ctx* c, int pipeline) {
-    if (!c || pipeline < 0 || pipeline > 1) return LYON_ERR_INVALID_ARGUMENT;
+    if (!c || pipeline < 0 || pipeline > 2) return LYON_ERR_INVALID_ARGUMENT;
     c->tile_force_general = pipeline == 1;
+    c->wt_mode = pipeline == 2 ? 1 : 0;  // 2: warp-owned tiles instead of CTA-owned ones (experiment)
+    if (pipeline == 0)
+        if (const char* e = getenv("LYON_PIPE")) c->wt_mode = strcmp(e, "wtile") == 0 ? 1 : 0;
     return LYON_OK;
 }
 
@@ -1939,6 +2096,10 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyo
     if (o->tolerance != o->tolerance) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN
     if (o->start_cap > 2 || o->end_cap > 2 || o->line_join > 3) return LYON_ERR_INVALID_ARGUMENT;
     if ((vertex_capacity && !d_vertices) || (index_capacity && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_vertices) & 31u) {
+        c->err = "d_vertices must be 32-byte aligned (vertices leave the SM as 256-bit stores)";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
     bool usable = false;
     const bool vw = o->variable_line_width >= 0 && b->num_attributes > 0;  // thread-per-path kernels: plan, then emit
     if (!vw && b->n_paths && b->n_verbs) {
@@ -1958,6 +2119,24 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyo
     TRY((tile_launch<TILE_MODE_FUSED>(c, (GpuVertex*)d_vertices, d_indices, vertex_capacity, index_capacity / 3ull, vertex_base,
                                       d_path_vertex_end, d_path_index_end)));
     TRY(fetch_tile_totals(c));
+    if (c->tile_is_wtile && (c->h_tile_totals->error & TILE_ERR_WT_OVERFLOW)) {
+        // a join or cap with more than 65535 vertices: warp tiles keep 16-bit offsets, CTA tiles do not
+        TRY(tile_prepass(c, b, &usable, false));
+        if (!usable) {
+            uint64_t nv = 0, ni = 0;
+            c->tile_force_general ^= 2;  // plan through the general pipeline
+            const int st = lyon_cuda_stroke_plan(c, b, o, &nv, &ni);
+            c->tile_force_general ^= 2;
+            TRY(st);
+            *n_vertices = nv;
+            *n_indices = ni;
+            if (nv > vertex_capacity || ni > index_capacity) return LYON_ERR_BUFFER_TOO_SMALL;
+            return lyon_cuda_stroke_emit(c, d_vertices, d_indices, vertex_base, d_path_vertex_end, d_path_index_end);
+        }
+        TRY((tile_launch<TILE_MODE_FUSED>(c, (GpuVertex*)d_vertices, d_indices, vertex_capacity, index_capacity / 3ull, vertex_base,
+                                          d_path_vertex_end, d_path_index_end)));
+        TRY(fetch_tile_totals(c));
+    }
     TRY(tile_error(c));
     const uint64_t nv = c->h_tile_totals->vertices, nt = c->h_tile_totals->triangles;
     if (nv > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || (nv && vertex_base + nv - 1ull > 0xFFFFFFFEull)) return LYON_ERR_TOO_MANY_VERTICES;

@@ -550,7 +550,7 @@ LYC_HD ArcNode arc_node(float a0, float a1, uint32_t va, uint32_t vb, uint32_t t
 }
 LYC_HD V2 arc_normal(float mid) { return libm_cos_sin(mid); }  // vector(mid.cos(), mid.sin()), stroke.rs:2627
 struct EmitSink {
-    GpuVertex* vtx;  // first vertex owned by this slot (global memory, or the shared-memory staging window)
+    GpuVertex* vtx;  // first vertex owned by this slot (global memory)
     uint32_t* idx;   // first index owned by this slot
     uint32_t nv, nt, base;
     LYC_HD uint32_t next_id() const { return base + nv; }
@@ -604,6 +604,25 @@ LYC_HD void EmitSink::arc(const VertexTemplate& vt, bool negative, float a0, flo
     nv += total;
     nt += total;
 }
+
+// The sink of the tile kernels' fast-join pass: one 256-bit store per 32-byte vertex (SASS STG.E.ENL2.256) instead of two
+// 128-bit ones; the vertex array must be 32-byte aligned (checked by the C entry points).  Used ONLY where the store is
+// inlined into the kernel body: ptxas 12.9 miscompiles the same PTX inside out-of-line device functions (a 32-bit STG,
+// seen in round 2; tools/check_sass.py looks for that pattern in the library that ships).
+struct EmitSinkWide : EmitSink {
+    LYC_HD uint32_t add_vertex(const VertexTemplate& vt, V2 normal, bool negative) {
+#ifdef __CUDA_ARCH__
+        const float srcbits = __uint_as_float((vt.src & 0x7FFFFFFFu) | (negative ? SIDE_NEG_BIT : 0u));
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(__cvta_generic_to_global(vtx + nv)),
+                     "f"(vt.position_on_path.x), "f"(vt.position_on_path.y), "f"(normal.x), "f"(normal.y), "f"(vt.advancement),
+                     "f"(vt.half_width), "f"(srcbits), "f"(vt.t)
+                     : "memory");
+        return base + nv++;
+#else
+        return EmitSink::add_vertex(vt, normal, negative);
+#endif
+    }
+};
 
 // stroke.rs:1869-1904.  (ids of p0 after its join, ids of p1 before its join, with the fold remaps)
 template <class Sink>

@@ -192,6 +192,80 @@ LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t ver
     }
 }
 
+// Phase 1a, complete (thread per verb): every slot of verb `verb` finished in one loop -- accumulated parameter, position
+// from the polynomial form held in registers (cubic_bezier.rs:1318-1365 / quadratic_bezier.rs:891-939; the last point is
+// the exact endpoint), flags, EndpointId and |P - prev| with the "maybe mergeable" flag.  The per-verb loop costs a FADD, a
+// Horner evaluation and a square root per point; evaluating slot by slot afterwards (tile_eval_slot) re-derives the
+// polynomial and re-loads the control points for every point, four times the instructions.  Split quadratics are not
+// handled here (tile_gen_split_slot).  `n` = the verb's Wang count (pre-pass).
+LYC_HD void tile_gen_verb_full(const TileViews& w, const StrokeParams& p, uint8_t verb, const V2* points, uint32_t pt, float n,
+                               uint32_t s0, uint32_t src) {
+    if (verb == VERB_END || verb == VERB_CLOSE) {
+        w.t[s0] = 1.0f;
+        w.flags[s0] = (uint8_t)(TF_END | (verb == VERB_CLOSE ? TF_CLOSE : 0));
+        w.src[s0] = src;
+        w.len()[s0] = 0.0f;  // pos / adv: the sub-path record, written by the walk
+        return;
+    }
+    const bool curve = verb == VERB_QUAD || verb == VERB_CUBIC, cubic = verb == VERB_CUBIC;
+    const uint32_t npts = cubic ? 3u : (curve ? 2u : 1u);
+    const V2 to = points[pt + npts - 1u];
+    if (verb == VERB_BEGIN) {
+        w.pos[s0] = to;
+        w.t[s0] = 1.0f;
+        w.flags[s0] = TF_BEGIN;
+        w.src[s0] = src;
+        w.len()[s0] = 0.0f;
+        return;
+    }
+    const V2 from = seg_from_point(points, pt, p.attr_stride);
+    uint32_t cnt = 1u;
+    float step = 0.0f;
+    V2 a1 = v2(0.0f, 0.0f), a2 = a1, a3 = a1;
+    if (curve) {
+        cnt = to_u32_or_1(n);
+        step = 1.0f / n;
+        const V2 c1 = points[pt];
+        if (cubic) {
+            const CubicPoly q = cubic_poly(from, c1, points[pt + 1], to);
+            a1 = q.a1;
+            a2 = q.a2;
+            a3 = q.a3;
+        } else {
+            const QuadPoly q = quad_poly(from, c1, to);
+            a1 = q.a1;
+            a2 = q.a2;
+        }
+    }
+    float t = 0.0f;
+    V2 prev = from;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        V2 pos = to;
+        float ts = 1.0f;
+        if (k + 1u < cnt) {
+            t = t + step;
+            ts = t;
+            // Horner as the reference has it: v = a0; v += a1*t; v += a2*t^2; [v += a3*t^3]
+            float u = t;
+            V2 v = from + a1 * u;
+            u = u * t;
+            v = v + a2 * u;
+            if (cubic) {
+                u = u * t;
+                v = v + a3 * u;
+            }
+            pos = v;
+        }
+        const uint32_t s = s0 + k;
+        w.pos[s] = pos;
+        w.t[s] = ts;
+        w.flags[s] = (uint8_t)(ts != 1.0f ? TF_FS : 0);
+        w.src[s] = src;
+        w.len()[s] = tile_len_flagged(p, pos, prev);
+        prev = pos;
+    }
+}
+
 // Phase 1b (thread per slot): position of a slot and its distance to the previous fed point.  Curve samples come from
 // the polynomial form (cubic_bezier.rs:1318-1365 / quadratic_bezier.rs:891-939; the last point of a curve is the exact
 // endpoint); the previous sample of the same curve is re-evaluated rather than read, so the phase needs no ordering.
@@ -247,7 +321,8 @@ LYC_HD void tile_eval_slot(const TileViews& w, const StrokeParams& p, const V2* 
 }
 // Phase 1c: a slot is "special" for the walk when it is not an ordinary kept point: Begin, End, or possibly within
 // the merge distance of its predecessor.
-LYC_HD bool tile_slot_special(const TileViews& w, uint32_t s) {
+template <class W>
+LYC_HD bool tile_slot_special(const W& w, uint32_t s) {
     return (w.flags[s] & (TF_BEGIN | TF_END)) != 0 || len_flagged(w.len()[s]);
 }
 
@@ -256,7 +331,8 @@ LYC_HD bool tile_slot_special(const TileViews& w, uint32_t s) {
 // the pair is NOT within the merge distance the slot is an ordinary kept point after all: its length loses the flag
 // and the caller clears its special bit, so it no longer interrupts the walk's 32-point steps.  Slots may be resolved
 // concurrently: a neighbour seen still flagged only leaves this slot to the walk's general step (same result).
-LYC_HD bool tile_resolve_flagged(const TileViews& w, const StrokeParams& p, uint32_t s) {
+template <class W>
+LYC_HD bool tile_resolve_flagged(const W& w, const StrokeParams& p, uint32_t s) {
     if (s == 0u) return false;
     if (w.flags[s] & (TF_BEGIN | TF_END)) return false;
     if (!len_flagged(w.len()[s])) return false;
@@ -274,7 +350,8 @@ LYC_HD bool tile_resolve_flagged(const TileViews& w, const StrokeParams& p, uint
 // 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), may_need_empty_cap (stroke.rs:1180,
 // 1533).  `special` holds one bit per slot (phase 1c): aligned groups of 32 ordinary points -- the overwhelmingly
 // common case -- reduce to the bare f32 addition chain on vector loads/stores.
-LYC_HD void tile_path_walk(const TileViews& w, const StrokeParams& p, uint32_t sa, uint32_t sb, const uint32_t* special) {
+template <class W>
+LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint32_t sb, const uint32_t* special) {
     const float nan = u2f(0x7FC00000u);
     float carry = 0.0f, adv = 0.0f;
     uint32_t begin_slot = sa, last_kept = sa, m = 0;

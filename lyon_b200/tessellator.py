@@ -185,10 +185,11 @@ class DeviceTessellator:
             _raise(self.L, self.ctx, st)
         return out
 
-    def set_pipeline(self, general: bool):
-        """False: automatic (fused shared-memory tile pipeline when every path fits a tile); True: always the
-        general multi-kernel pipeline.  Both produce identical output."""
-        st = self.L.lyon_cuda_set_pipeline(self.ctx, 1 if general else 0)
+    def set_pipeline(self, general):
+        """False / 0: automatic (shared-memory tiles owned by a CTA when every path fits one, else the general
+        pipeline); True / 1: always the general multi-kernel pipeline; 2: tiles owned by a single warp where they fit
+        (an experiment kept for comparison, slower).  All produce identical output."""
+        st = self.L.lyon_cuda_set_pipeline(self.ctx, int(general))
         if st != 0:
             _raise(self.L, self.ctx, st)
 

@@ -80,11 +80,29 @@ static inline float angle_to(float self, float to) {
 
 // libm calls (Rust f32::{sin,cos,acos,asin,log2} -> platform libm).  Evaluated in double and
 // rounded once so that host and device agree (see DESIGN.md "Transcendentals").
-static inline float libm_cos(float a) { return (float)cos((double)a); }
-static inline float libm_sin(float a) { return (float)sin((double)a); }
-static inline float libm_acos(float a) { return (float)acos((double)a); }
-static inline float libm_asin(float a) { return (float)asin((double)a); }
-static inline float libm_log2(float a) { return (float)log2((double)a); }
+// Every call can be recorded (function code + argument) for tests/test_libm_pinning.py, which compares this
+// convention with the platform's own f32 routines (what rustc-built lyon would call) on the arguments that
+// actually occur: 0 cos, 1 sin (arc vertices, variable-width side normals), 2 acos, 3 asin, 4 log2, 5 cos / 6 sin of
+// find_sharp_turn's rotation.
+struct LibmTrace {
+    std::vector<uint8_t> fn;
+    std::vector<float> arg;
+};
+static thread_local LibmTrace* g_libm_trace = nullptr;
+static inline void libm_note(uint8_t fn, float a) {
+    if (g_libm_trace) {
+        g_libm_trace->fn.push_back(fn);
+        g_libm_trace->arg.push_back(a);
+    }
+}
+// g_libm_platform_f32 (tests only, oracle_set_libm_mode): call the platform's f32 routines instead -- what a rustc build
+// of lyon does on this host -- so that the whole oracle can be run under both conventions and the meshes compared.
+static thread_local bool g_libm_platform_f32 = false;
+static inline float libm_cos(float a, uint8_t code = 0) { libm_note(code, a); return g_libm_platform_f32 ? cosf(a) : (float)cos((double)a); }
+static inline float libm_sin(float a, uint8_t code = 1) { libm_note(code, a); return g_libm_platform_f32 ? sinf(a) : (float)sin((double)a); }
+static inline float libm_acos(float a) { libm_note(2, a); return g_libm_platform_f32 ? acosf(a) : (float)acos((double)a); }
+static inline float libm_asin(float a) { libm_note(3, a); return g_libm_platform_f32 ? asinf(a) : (float)asin((double)a); }
+static inline float libm_log2(float a) { libm_note(4, a); return g_libm_platform_f32 ? log2f(a) : (float)log2((double)a); }
 
 // Rust `x as u32` (saturating; NaN -> 0).
 static inline uint32_t sat_u32(float v) {
@@ -240,7 +258,7 @@ static inline bool find_sharp_turn(V2 from, V2 ctrl, V2 to, float* t_out) {
     }
     // euclid Rotation2D::new(-angle).transform_vector: (x*cos - y*sin, y*cos + x*sin)
     float ang = -angle_from_x_axis(long_axis);
-    float s = libm_sin(ang), c = libm_cos(ang);
+    float s = libm_sin(ang, 6), c = libm_cos(ang, 5);  // traced apart: this rotation decides t_split, hence flatten counts
     V2 rctrl = v2(v.x * c - v.y * s, v.y * c + v.x * s);
     V2 rto = v2(baseline.x * c - baseline.y * s, baseline.y * c + baseline.x * s);
     return quad_local_x_extremum_t(v2(0.0f, 0.0f), rctrl, rto, t_out);

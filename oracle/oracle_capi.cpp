@@ -302,4 +302,23 @@ int oracle_line_intersection(const float* a, const float* b, float* out) {
     out[1] = o.y;
     return ok ? 1 : 0;
 }
+// 0: transcendental calls evaluated in double and rounded once (default, what the device does); 1: the platform's f32 libm
+void oracle_set_libm_mode(int platform_f32) { g_libm_platform_f32 = platform_f32 != 0; }
+// libm trace (tests/test_libm_pinning.py): record every libm call of the calling thread between begin and end.
+static LibmTrace g_trace_store;
+void oracle_libm_trace_begin() {
+    g_trace_store.fn.clear();
+    g_trace_store.arg.clear();
+    g_libm_trace = &g_trace_store;
+}
+uint64_t oracle_libm_trace_end() {
+    g_libm_trace = nullptr;
+    return g_trace_store.fn.size();
+}
+void oracle_libm_trace_copy(uint8_t* fn, float* arg) {
+    if (!g_trace_store.fn.empty()) {
+        memcpy(fn, g_trace_store.fn.data(), g_trace_store.fn.size());
+        memcpy(arg, g_trace_store.arg.data(), g_trace_store.arg.size() * 4);
+    }
+}
 }  // extern "C"

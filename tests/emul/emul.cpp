@@ -10,6 +10,7 @@
 
 #include "../../include/lyon_cuda.h"
 #include "../../lyon_b200/csrc/stroke_tile.cuh"
+#include "../../lyon_b200/csrc/stroke_wtile.cuh"
 #include "../../lyon_b200/csrc/stroke_vw.cuh"
 
 using namespace lyc;
@@ -175,14 +176,14 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         uint32_t ncurve = verb == VERB_QUAD ? 2u : (verb == VERB_CUBIC ? 3u : 1u);
         uint32_t vb = b->path_verb_begin[verb_path[v]];
         uint32_t id = p.num_attributes > 0 ? (seg_pt[v] - seg_pt[vb]) + ncurve - 1u : evt_before[v] - evt_before[vb];
-        if (verb == VERB_QUAD && plans[v].tsplit >= 0.0f) {  // the tile kernel's warp-per-split-quadratic route
-            for (uint32_t lane = 0; lane < 8u; ++lane) tile_gen_split_quad(w, p, points, seg_pt[v], seg_off[v], id, lane, 8u);
+        if (verb == VERB_QUAD && plans[v].tsplit >= 0.0f) {  // split quadratic: a lane per slot from the pre-pass's plan
+            const SplitRec rec{plans[v].tsplit, plans[v].n_a, plans[v].n_b, 0.0f};
+            for (uint32_t j = 0; j < plans[v].nslots; ++j) tile_gen_split_slot(w, p, points, seg_pt[v], seg_off[v], id, rec, j);
             continue;
         }
-        tile_gen_verb(w, p, verb, points, seg_pt[v], plans[v], seg_off[v], id);
+        tile_gen_verb_full(w, p, verb, points, seg_pt[v], plans[v].n_a, seg_off[v], id);
     }
-    // phase 1b: curve positions per slot; 1c: special mask
-    for (uint32_t s = 0; s < NS; ++s) tile_eval_slot(w, p, points, s);
+    // phase 1c: special mask (phase 1a leaves the slots complete)
     std::vector<uint32_t> special(NS / 32 + 2, 0);
     for (uint32_t s = 0; s < NS; ++s)
         if (tile_slot_special(w, s)) special[s >> 5] |= 1u << (s & 31u);
@@ -213,12 +214,10 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
                 count_full_join(w, p, s, c.pk, c.nk, &nv, &nt, &code);
             }
         } else if (c.kind == KIND_END) {
-            CountSink sink;
-            sink.nv = sink.nt = 0;
-            sink.base = 0;
-            stroke_end_slot(w, p, s, 0u, sink);
-            nv = sink.nv;
-            nt = sink.nt;
+            end_slot_count(w, p, s, &nv, &nt);
+            uint32_t gv, gt;
+            end_slot_count_generic(w, p, s, &gv, &gt);
+            if (gv != nv || gt != nt) return LYON_ERR_INTERNAL;  // the cheap End count must agree with the real routine
         }
         cnt_v[s] = nv;
         cnt_t[s] = nt;
@@ -247,8 +246,25 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         sink.idx = I + 3ull * toff[s];
         sink.nv = sink.nt = 0;
         sink.base = (uint32_t)vertex_base + voff[s];
-        if (w.F(s) & SEG_END_BIT) {
-            stroke_end_slot(w, p, s, (uint32_t)vertex_base, sink);
+        if (w.F(s) & SEG_END_BIT) {  // as the kernels do: an EndRecord, then stroke_end_slot on the record alone
+            EndRecord rec;
+            end_record_fill(w, s, &rec);
+            const V2 sub = w.P(s);
+            const uint32_t b0 = f2u(sub.x), m = f2u(sub.y) & 3u;
+            uint32_t q1 = b0, q4 = b0;
+            if (m >= 2u) {
+                q1 = next_kept_or_end(w, b0);
+                uint32_t l1 = s - 1u;
+                while (slot_dropped(w, l1)) --l1;
+                q4 = prev_kept(w, l1);
+            }
+            rec.vo1 = (uint32_t)vertex_base + w.VO(q1);
+            rec.vo4 = (uint32_t)vertex_base + w.VO(q4);
+            rec.first_id = sink.base;
+            EndRecView rv;
+            rv.r = &rec;
+            rv.n_slots = 7u;
+            stroke_end_slot(rv, p, 6u, 0u, sink);
         } else {
             uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
             if (jcode[s] & JC_FAST)
@@ -267,6 +283,225 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     *out_i = I;
     *n_v = tv;
     *n_i = 3ull * tt;
+    return status;
+}
+// The WARP-TILE pipeline (wtile_kernels.cuh), one tile per path: the per-item routines of stroke_wtile.cuh against
+// WTileViews -- slot -> verb lookup through the head mask, t / EndpointId re-derived per verb, 16-bit chunk-relative
+// offsets, the cheap End-slot count (checked here against the real routine), End slots emitted from EndRecords.
+extern "C" int emul_stroke_batch_wtile(const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t vertex_base,
+                                       lyon_stroke_vertex** out_v, uint64_t* n_v, uint32_t** out_i, uint64_t* n_i,
+                                       uint64_t* path_vertex_end, uint64_t* path_index_end) {
+    *out_v = nullptr;
+    *out_i = nullptr;
+    *n_v = *n_i = 0;
+    StrokeParams p = make_params(*o, b->num_attributes);
+    const V2* points = reinterpret_cast<const V2*>(b->points);
+    std::vector<GpuVertex> V;
+    std::vector<uint32_t> I;
+    int status = LYON_OK;
+    uint64_t V0 = 0, T0 = 0;
+    std::vector<SplitRec> split_rec;
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        const uint32_t va = b->path_verb_begin[path], vb = b->path_verb_begin[path + 1], nverbs = vb - va;
+        const uint32_t pt_path = b->path_point_begin[path];
+        // pre-pass + setup: per verb
+        std::vector<uint16_t> vs0(nverbs + 1), vword;
+        std::vector<uint32_t> vsrc(nverbs + 1), vptg(nverbs + 1);
+        std::vector<float> vstep(nverbs + 1);
+        std::vector<uint8_t> vkind(nverbs + 1);
+        uint32_t pt = pt_path, so = 0, ev = 0;
+        split_rec.clear();
+        for (uint32_t v = va; v < vb; ++v) {
+            const uint32_t vi = v - va;
+            const uint8_t verb = b->verbs[v];
+            const VerbPlan plan = plan_verb(verb, points, pt, p.attr_stride, p.tolerance);
+            const bool is_ev = verb != VERB_END && verb != VERB_CLOSE;
+            const uint32_t ncurve = verb == VERB_QUAD ? 2u : (verb == VERB_CUBIC ? 3u : 1u);
+            vs0[vi] = (uint16_t)so;
+            vptg[vi] = pt;
+            vsrc[vi] = !is_ev ? 0u : (p.num_attributes > 0 ? (pt - pt_path) + ncurve - 1u : ev);
+            vkind[vi] = verb;
+            vstep[vi] = 0.0f;
+            if (verb == VERB_QUAD || verb == VERB_CUBIC) {
+                if (plan.tsplit >= 0.0f) {
+                    vkind[vi] = (uint8_t)(verb | VK_SPLIT);
+                    vstep[vi] = u2f((uint32_t)split_rec.size());
+                    split_rec.push_back(SplitRec{plan.tsplit, plan.n_a, plan.n_b, 0.0f});
+                } else {
+                    vstep[vi] = 1.0f / plan.n_a;
+                }
+            }
+            so += plan.nslots;
+            pt += verb_point_count(verb, p.attr_stride);
+            ev += is_ev ? 1u : 0u;
+        }
+        if (so > 60000u) return LYON_ERR_INTERNAL;  // the emulation keeps one path per warp tile
+        const uint32_t NS = so;
+        vs0[nverbs] = (uint16_t)NS;
+        const uint32_t NW = NS / 32 + 2;
+        std::vector<uint32_t> head(NW, 0), special(NW, 0), cbase_v(NW, 0), cbase_t(NW, 0), off(NS + 40, 0);
+        vword.assign(NW, 0);
+        for (uint32_t vi = 0; vi < nverbs; ++vi) head[vs0[vi] >> 5] |= 1u << (vs0[vi] & 31u);
+        for (uint32_t i = 1; i < NW; ++i) vword[i] = (uint16_t)(vword[i - 1] + __builtin_popcount(head[i - 1]));
+        std::vector<V2> pos(NS + 40);
+        std::vector<float> adv(NS + 40);
+        std::vector<uint8_t> flags(NS + 40, TF_END), jcode(NS + 40, 0);
+        WTileViews w{};
+        w.pos = pos.data();
+        w.adv = adv.data();
+        w.off = off.data();
+        w.flags = flags.data();
+        w.jcode = jcode.data();
+        w.cbase_v = cbase_v.data();
+        w.cbase_t = cbase_t.data();
+        w.head = head.data();
+        w.vword = vword.data();
+        w.vs0 = vs0.data();
+        w.vstep = vstep.data();
+        w.vsrc = vsrc.data();
+        w.vkind = vkind.data();
+        w.split_rec = split_rec.data();
+        w.n_slots = NS;
+        // setup: split quadratics, a "lane" per slot
+        for (uint32_t vi = 0; vi < nverbs; ++vi)
+            if (vkind[vi] & VK_SPLIT)
+                for (uint32_t k = 0; k < (uint32_t)(vs0[vi + 1] - vs0[vi]); ++k)
+                    wt_gen_split_slot(w, p, points, vptg[vi], vs0[vi], split_rec[f2u(vstep[vi])], k);
+        // gen
+        std::vector<V2> from(NS + 1);
+        for (uint32_t s = 0; s < NS; ++s) {
+            const uint32_t vi = w.verb_of(s);
+            if (vkind[vi] & VK_SPLIT) continue;
+            wt_gen_slot(w, p, points, vkind[vi], vptg[vi], s - vs0[vi], (uint32_t)(vs0[vi + 1] - vs0[vi]), vstep[vi], s, &from[s]);
+        }
+        for (uint32_t s = 0; s < NS; ++s) {
+            const uint32_t vi = w.verb_of(s);
+            const uint8_t kind = vkind[vi];
+            if (kind & VK_SPLIT) continue;
+            float l = 0.0f;
+            if (kind != VERB_BEGIN && kind != VERB_END && kind != VERB_CLOSE)
+                l = tile_len_flagged(p, w.pos[s], s - vs0[vi] == 0u ? from[s] : w.pos[s - 1u]);
+            w.len()[s] = l;
+        }
+        for (uint32_t s = 0; s < NS; ++s)
+            if (tile_slot_special(w, s)) special[s >> 5] |= 1u << (s & 31u);
+        for (uint32_t pass = 0; pass < 2u; ++pass)
+            for (uint32_t s = 0; s < NS; ++s)
+                if (((special[s >> 5] >> (s & 31u)) & 1u) && ((s & 1u) == pass) && (s & 31u) != 0u && tile_resolve_flagged(w, p, s))
+                    special[s >> 5] &= ~(1u << (s & 31u));
+        // walk
+        if (NS) tile_path_walk(w, p, 0u, NS, special.data());
+        // classify + count (packed 16 + 16 bit counts in `off`)
+        std::vector<uint32_t> ends;
+        for (uint32_t s = 0; s < NS; ++s) {
+            const SlotClass c = classify_slot(w, s);
+            uint32_t nv = 0, nt = 0;
+            uint8_t code = 0;
+            if (c.kind == KIND_JOIN) {
+                if (join_is_fast(w.P(c.pk), w.P(s), w.P(c.nk), (c.sf & SEG_FS_BIT) != 0u)) {
+                    nv = 2u;
+                    nt = (w.F(c.pk) & SEG_BEGIN_BIT) ? 0u : 2u;
+                    code = JC_FAST | JC_SINGLE_POS | JC_SINGLE_NEG;
+                } else {
+                    count_full_join(w, p, s, c.pk, c.nk, &nv, &nt, &code);
+                }
+            } else if (c.kind == KIND_END) {
+                end_slot_count(w, p, s, &nv, &nt);
+                uint32_t gv, gt;
+                end_slot_count_generic(w, p, s, &gv, &gt);
+                if (gv != nv || gt != nt) status = LYON_ERR_INTERNAL;  // the cheap End count must agree with the real routine
+                ends.push_back(s);
+            }
+            if ((nv | nt) > 0xFFFFu) return LYON_ERR_INTERNAL;
+            off[s] = nv | (nt << 16);
+            jcode[s] = code;
+        }
+        // scan: chunk bases + 16-bit relative offsets
+        uint32_t run_v = 0, run_t = 0;
+        for (uint32_t c = 0; c <= NS; c += 32) {
+            cbase_v[c >> 5] = run_v;
+            cbase_t[c >> 5] = run_t;
+            uint32_t ev_ = 0, et_ = 0;
+            for (uint32_t s = c; s < c + 32 && s <= NS; ++s) {
+                const uint32_t cnt = s < NS ? off[s] : 0u;
+                if ((ev_ | et_) > 0xFFFFu) return LYON_ERR_INTERNAL;
+                off[s] = ev_ | (et_ << 16);
+                ev_ += cnt & 0xFFFFu;
+                et_ += cnt >> 16;
+            }
+            run_v += ev_;
+            run_t += et_;
+        }
+        const uint64_t tv = V0 + run_v, tt = T0 + run_t;
+        if (tv > 0xFFFFFFFFull || tt > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
+        if (tv && vertex_base + tv - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+        V.resize(tv);
+        I.resize(3 * tt);
+        const uint32_t gbase = (uint32_t)vertex_base + (uint32_t)V0;
+        GpuVertex* gv = V.data() + V0;
+        uint32_t* gi = I.data() + 3 * T0;
+        for (uint32_t s = 0; s < NS; ++s) {
+            if (w.F(s) & SEG_END_BIT) continue;
+            const uint32_t vo = w.VO(s), to = w.TO(s), nv = w.VO(s + 1) - vo, nt = w.TO(s + 1) - to;
+            if ((nv | nt) == 0) continue;
+            EmitSink sink;
+            sink.vtx = gv + vo;
+            sink.idx = gi + 3ull * to;
+            sink.nv = sink.nt = 0;
+            sink.base = gbase + vo;
+            const uint32_t pk = prev_kept(w, s), nk = next_kept_or_end(w, s);
+            if (jcode[s] & JC_FAST)
+                emit_fast_join(w, p, s, pk, nk, gbase, jcode.data(), sink);
+            else
+                emit_full_join(w, p, s, pk, nk, gbase, jcode.data(), sink);
+            if (sink.nv != nv || sink.nt != nt) status = LYON_ERR_INTERNAL;
+        }
+        // End slots: record, then the End kernel's routine on the record alone
+        for (uint32_t s : ends) {
+            const uint32_t vo = w.VO(s), to = w.TO(s), nv = w.VO(s + 1) - vo, nt = w.TO(s + 1) - to;
+            if ((nv | nt) == 0) continue;
+            EndRecord rec;
+            end_record_fill(w, s, &rec);
+            const V2 sub = w.P(s);
+            const uint32_t b0 = f2u(sub.x), m = f2u(sub.y) & 3u;
+            uint32_t q1 = b0, q4 = b0;
+            if (m >= 2u) {
+                q1 = next_kept_or_end(w, b0);
+                uint32_t l1 = s - 1u;
+                while (slot_dropped(w, l1)) --l1;
+                q4 = prev_kept(w, l1);
+            }
+            rec.vo1 = gbase + w.VO(q1);
+            rec.vo4 = gbase + w.VO(q4);
+            rec.first_id = gbase + vo;
+            rec.nv = nv;
+            rec.nt = nt;
+            rec.vtx_index = V0 + vo;
+            rec.tri_index = T0 + to;
+            EndRecView rv;
+            rv.r = &rec;
+            rv.n_slots = 7u;
+            EmitSink sink;
+            sink.vtx = V.data() + rec.vtx_index;
+            sink.idx = I.data() + 3ull * rec.tri_index;
+            sink.nv = sink.nt = 0;
+            sink.base = rec.first_id;
+            stroke_end_slot(rv, p, 6u, 0u, sink);
+            if (sink.nv != rec.nv || sink.nt != rec.nt) status = LYON_ERR_INTERNAL;
+        }
+        V0 = tv;
+        T0 = tt;
+        if (path_vertex_end) path_vertex_end[path] = V0;
+        if (path_index_end) path_index_end[path] = 3ull * T0;
+    }
+    GpuVertex* Vout = (GpuVertex*)malloc((V.size() ? V.size() : 1) * sizeof(GpuVertex));
+    uint32_t* Iout = (uint32_t*)malloc((I.size() ? I.size() : 1) * 4);
+    if (!V.empty()) memcpy(Vout, V.data(), V.size() * sizeof(GpuVertex));
+    if (!I.empty()) memcpy(Iout, I.data(), I.size() * 4);
+    *out_v = (lyon_stroke_vertex*)Vout;
+    *out_i = Iout;
+    *n_v = V.size();
+    *n_i = I.size();
     return status;
 }
 extern "C" void emul_free(void* p) { free(p); }

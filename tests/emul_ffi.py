@@ -33,6 +33,8 @@ def lib():
                                         ctypes.c_void_p, ctypes.c_void_p]
         L.emul_stroke_batch_tile.restype = ctypes.c_int
         L.emul_stroke_batch_tile.argtypes = L.emul_stroke_batch.argtypes
+        L.emul_stroke_batch_wtile.restype = ctypes.c_int
+        L.emul_stroke_batch_wtile.argtypes = L.emul_stroke_batch.argtypes
         L.emul_stroke_batch_vw.restype = ctypes.c_int
         L.emul_stroke_batch_vw.argtypes = L.emul_stroke_batch.argtypes
         L.emul_free.argtypes = [ctypes.c_void_p]
@@ -54,7 +56,8 @@ PIPELINE = "general"  # or "tile": which device pipeline's per-item code stroke_
 
 def stroke_batch(batch: PathBatch, opts: StrokeOptions, vertex_base: int = 0, with_ranges=False, pipeline=None):
     L = lib()
-    fn = L.emul_stroke_batch_tile if (pipeline or PIPELINE) == "tile" else L.emul_stroke_batch
+    which = pipeline or PIPELINE
+    fn = {"tile": L.emul_stroke_batch_tile, "wtile": L.emul_stroke_batch_wtile}.get(which, L.emul_stroke_batch)
     if opts.variable_line_width is not None and batch.num_attributes > 0:
         fn = L.emul_stroke_batch_vw  # variable width: the thread-per-path state machine, whatever the pipeline
     verbs = np.ascontiguousarray(batch.verbs, np.uint8)

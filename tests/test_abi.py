@@ -1,5 +1,6 @@
 """The C-ABI library loads and exports every symbol include/lyon_cuda.h declares (no compute without a GPU)."""
 import re
+from pathlib import Path
 
 import pytest
 
@@ -45,3 +46,18 @@ def test_product_does_not_reference_the_oracle():
             txt = f.read_text()
             for needle in ("liblyon_oracle", "libemul", "oracle_ffi", "emul_ffi", "lyon_oracle.hpp"):
                 assert needle not in txt, f"{f} references test infrastructure ({needle})"
+
+
+def test_wide_vertex_stores_survive_ptxas():
+    """The fast-join pass writes each 32-byte vertex with one 256-bit store; ptxas 12.9 was seen to turn the same PTX into
+    a 32-bit store in out-of-line code (tools/check_sass.py).  The library that ships must contain the real thing."""
+    import shutil
+    import subprocess
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    root = Path(__file__).resolve().parent.parent
+    import __graft_entry__ as g
+    lib = g.build_cuda()
+    r = subprocess.run([sys.executable, str(root / "tools" / "check_sass.py"), str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

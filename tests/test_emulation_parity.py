@@ -13,7 +13,7 @@ from parity import assert_mesh_parity, bbox_extent
 GOLDEN = O.ROOT / "tests" / "golden"
 
 
-@pytest.fixture(autouse=True, params=["general", "tile"])
+@pytest.fixture(autouse=True, params=["general", "tile", "wtile"])
 def pipeline(request, monkeypatch):
     """Every test runs against both device pipelines' per-item code: the general multi-kernel one
     (stroke_core.cuh / Views) and the fused tile one (stroke_tile.cuh / TileViews)."""

@@ -25,10 +25,11 @@ def tz():
 ROUTE = "tile"
 
 
-@pytest.fixture(autouse=True, params=["tile", "fused", "general"])
+@pytest.fixture(autouse=True, params=["tile", "fused", "wtile", "wfused", "general"])
 def route(request):
-    """Every stroke test runs three ways: plan+emit through the shared-memory tile pipeline, the single-pass
-    fused call, and plan+emit through the general multi-kernel pipeline (any path length)."""
+    """Every stroke test runs five ways: plan+emit and the single-pass fused call through the automatic choice
+    (shared-memory tiles owned by a CTA when the paths fit), the same two through the warp-owned tile kernel (kept as a
+    measured experiment), and plan+emit through the general multi-kernel pipeline (any path length)."""
     global ROUTE
     ROUTE = request.param
     yield request.param
@@ -39,9 +40,9 @@ def gpu_stroke(tz, batch, o, vertex_base=0, with_ranges=False):
     import torch
     from lyon_b200 import device_mesh_to_host
     d = tz.upload(batch)
-    tz.set_pipeline(ROUTE == "general")
+    tz.set_pipeline(1 if ROUTE == "general" else (2 if ROUTE in ("wtile", "wfused") else 0))
     try:
-        if ROUTE == "fused":
+        if ROUTE in ("fused", "wfused"):
             out = tz.stroke_fused(d, o, vertex_base=vertex_base, with_ranges=with_ranges)
         else:
             out = tz.stroke(d, o, vertex_base=vertex_base, with_ranges=with_ranges)

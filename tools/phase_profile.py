@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of k_stroke_tile on a C3 sample (needs a -DLYON_PHASE_TIMING build, see dev_build.sh).
+"""Per-phase cycle breakdown of the stroke tile kernel on a C3 sample (needs a -DLYON_PHASE_TIMING build, dev_build.sh).
 
   LYON_CUDA_LIB=lyon_b200/liblyon_cuda_phase.so python tools/phase_profile.py [n_paths]
+  LYON_PIPE=ctile ...   the CTA-tile kernel (k_stroke_tile) instead of the warp-tile kernel (k_stroke_wtile)
 """
 import ctypes
+import os
 import sys
 from pathlib import Path
 
@@ -15,12 +17,15 @@ import torch  # noqa: E402
 import workloads as W  # noqa: E402
 from lyon_b200 import DeviceTessellator, LineCap, LineJoin, StrokeOptions  # noqa: E402
 
-NAMES = ["0 ticket", "1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
-         "6 fast emit", "6 full/end emit", "0 stage (TMA wait)"]
+NAMES_CTILE = ["0 ticket", "1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
+               "6 fast emit", "6 full/end emit", "0 stage (TMA wait)"]
+NAMES_WTILE = ["0 ticket+header", "0 stage (TMA)", "1 setup (verbs)", "2 gen (slots)", "3 walk", "4 classify", "4 dense count",
+               "5 scan", "6 lookback", "7 fast emit", "7 full emit", "7 end records"]
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+    names = NAMES_CTILE if os.environ.get("LYON_PIPE") == "ctile" else NAMES_WTILE
     tz = DeviceTessellator(0)
     batch = W.c3_batch_range(0, n, 64)
     opts = StrokeOptions(line_width=2.0, line_join=LineJoin.Round, tolerance=0.1).with_line_cap(LineCap.Round)
@@ -38,7 +43,7 @@ def main():
     tz.L.lyon_cuda_debug_phase_cycles(tz.ctx, out)
     tot = sum(out[:12])
     print(f"paths {n} vertices {v.shape[0]} kernel {ms:.3f} ms")
-    for k, name in enumerate(NAMES):
+    for k, name in enumerate(names):
         print(f"  {name:18s} {out[k] / tot * 100:6.2f} %   {out[k]:>14d} cycles")
 
 
