@@ -353,7 +353,7 @@ def test_svg_arc_to_arc_round_trip():
             c, r, start, sw, xr = svg_arc_to_arc(frm, to, (40.0, 30.0), f(0.3), large, sweep)
             quads = arc_to_quadratics(c, r, start, sw, xr)
             assert quads and quads[-1][2] == f(1.0)
-            assert np.allclose(quads[-1][1], to, atol=1e-3)
+            assert np.allclose(quads[-1][1], to, atol=0.03)  # fast_atan2: 2.5e-4 rad x radius 40
             assert (abs(sw) > np.pi) == large
             assert (sw > 0) == sweep
 
