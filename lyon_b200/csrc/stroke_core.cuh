@@ -79,15 +79,61 @@ struct Views {
 // slot indices are tile-relative, flags are one byte (SEG_*_BIT >> 24), the endpoint id is stored per slot.
 static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08, TF_EVAL = 0x04, TF_CUBIC = 0x02,
                      TF_LAST = 0x01;
+// One slot array of a CTA tile.  Under nvcc it is a 32-bit byte offset into the CTA's dynamic shared memory: the accessors
+// go through the `extern __shared__` symbol, so every access compiles to LDS / STS with 32-bit address arithmetic (a
+// pointer kept in a struct that is passed to out-of-line routines degrades to generic LD / ST with 64-bit address
+// arithmetic: 15 % of the tile kernel's instructions in round 1).  On the CPU (tests/emul) it is a plain pointer.
+#ifdef __CUDACC__
+extern __shared__ __align__(16) unsigned char lyc_tile_smem[];
+template <class T>
+struct TArr {
+    uint32_t off;
+    __host__ __device__ __forceinline__ T* ptr() const {
+#ifdef __CUDA_ARCH__
+        return reinterpret_cast<T*>(lyc_tile_smem + off);
+#else
+        return nullptr;
+#endif
+    }
+    __host__ __device__ __forceinline__ T& operator[](uint32_t i) const { return ptr()[i]; }
+    __host__ __device__ __forceinline__ T* operator+(uint32_t i) const { return ptr() + i; }
+    __host__ __device__ __forceinline__ explicit operator bool() const { return true; }
+    template <class U>
+    __host__ __device__ __forceinline__ TArr<U> as() const {
+        TArr<U> r;
+        r.off = off;
+        return r;
+    }
+};
+#else
+template <class T>
+struct TArr {
+    T* p;
+    TArr& operator=(T* q) {
+        p = q;
+        return *this;
+    }
+    T* ptr() const { return p; }
+    T& operator[](uint32_t i) const { return p[i]; }
+    T* operator+(uint32_t i) const { return p + i; }
+    explicit operator bool() const { return p != nullptr; }
+    template <class U>
+    TArr<U> as() const {
+        TArr<U> r;
+        r.p = reinterpret_cast<U*>(p);
+        return r;
+    }
+};
+#endif
 struct TileViews {
-    V2* pos;
-    float* t;
-    float* adv;
-    uint32_t* src;   // EndpointId of the slot's vertex source
-    uint8_t* flags;  // TF_*
-    uint32_t* voff;  // aliased by `len` until the count phase
-    uint32_t* toff;
-    uint8_t* jcode;
+    TArr<V2> pos;
+    TArr<float> t;
+    TArr<float> adv;
+    TArr<uint32_t> src;   // EndpointId of the slot's vertex source
+    TArr<uint8_t> flags;  // TF_*
+    TArr<uint32_t> voff;  // aliased by `len` until the count phase
+    TArr<uint32_t> toff;
+    TArr<uint8_t> jcode;
     uint32_t n_slots;
     LYC_HD V2 P(uint32_t s) const { return pos[s]; }
     LYC_HD float A(uint32_t s) const { return adv[s]; }
@@ -95,7 +141,7 @@ struct TileViews {
     LYC_HD uint32_t F(uint32_t s) const { return (uint32_t)flags[s] << 24; }
     LYC_HD uint32_t SRC(uint32_t s) const { return src[s]; }
     LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
-    LYC_HD float* len() const { return reinterpret_cast<float*>(voff); }
+    LYC_HD TArr<float> len() const { return voff.as<float>(); }
 };
 
 LYC_HD uint32_t verb_point_count(uint8_t verb, uint32_t a) {
@@ -843,9 +889,9 @@ LYC_HD void stroke_end_slot(const W& w, const StrokeParams& o, uint32_t s, uint3
 
 // Edge triangles between the previous stream join (at kept slot pk, not a Begin) and join j at slot s.
 // With a jcode array (emit pass) the previous join's vertex layout is decoded, otherwise it is recomputed.
-template <class Sink, class W>
+template <class Sink, class W, class JC>
 LYC_HD void edge_to_previous_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t global_base,
-                                  const uint8_t* jcode, const Join& j, Sink& sink) {
+                                  JC jcode, const Join& j, Sink& sink) {
     Join jp;
     if (jcode) {
         join_decode_ids(jp, jcode[pk], slot_vertex_base<Sink>(w, pk, global_base));
@@ -905,9 +951,9 @@ LYC_HD void count_full_join(const W& w, const StrokeParams& o, uint32_t s, uint3
     *code = join_encode(j);
 }
 // Emit pass of a fast join (flattened_step, stroke.rs:1743-1806).
-template <class Sink, class W>
+template <class Sink, class W, class JC>
 LYC_HD void emit_fast_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t global_base,
-                           const uint8_t* jcode, Sink& sink) {
+                           JC jcode, Sink& sink) {
     const V2 normal = fast_join_normal(w.P(pk), w.P(s), w.P(nk));
     VertexTemplate vt = slot_vertex_template(w, o, s);
     Join j;
@@ -922,9 +968,9 @@ LYC_HD void emit_fast_join(const W& w, const StrokeParams& o, uint32_t s, uint32
     }
 }
 // Emit pass of any other stream join.
-template <class Sink, class W>
+template <class Sink, class W, class JC>
 LYC_HD void emit_full_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t global_base,
-                           const uint8_t* jcode, Sink& sink) {
+                           JC jcode, Sink& sink) {
     Join j;
     stream_join(w, o, s, pk, nk, j);
     VertexTemplate vt = slot_vertex_template(w, o, s);

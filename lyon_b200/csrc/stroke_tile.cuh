@@ -350,13 +350,13 @@ LYC_HD bool tile_resolve_flagged(const W& w, const StrokeParams& p, uint32_t s) 
 // 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), may_need_empty_cap (stroke.rs:1180,
 // 1533).  `special` holds one bit per slot (phase 1c): aligned groups of 32 ordinary points -- the overwhelmingly
 // common case -- reduce to the bare f32 addition chain on vector loads/stores.
-template <class W>
-LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint32_t sb, const uint32_t* special) {
+template <class W, class SP>
+LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint32_t sb, SP special) {
     const float nan = u2f(0x7FC00000u);
     float carry = 0.0f, adv = 0.0f;
     uint32_t begin_slot = sa, last_kept = sa, m = 0;
     bool mnec = false;
-    float* len = w.len();
+    const auto len = w.len();
     uint32_t s = sa;
     while (s < sb) {
 #ifdef __CUDA_ARCH__
@@ -369,7 +369,7 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
             if (bits == 0u) {
                 float4 l[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(len + s + 4 * q);
+                for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(&len[s + 4 * q]);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     l[q].x = adv = adv + l[q].x;
@@ -378,7 +378,7 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
                     l[q].w = adv = adv + l[q].w;
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(w.adv + s + 4 * q) = l[q];
+                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&w.adv[s + 4 * q]) = l[q];
                 m += 32u;
                 last_kept = s + 31u;
                 s += 32u;
@@ -392,7 +392,7 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
             uint32_t word = special[s >> 5] >> (s & 31u);
             uint32_t left = 32u - (s & 31u);
             if ((word & 0xFu) == 0u) {
-                float4 l = *reinterpret_cast<const float4*>(len + s);
+                float4 l = *reinterpret_cast<const float4*>(&len[s]);
                 const uint32_t s_in = s;
                 for (;;) {
                     const uint32_t s2 = s + 4u;
@@ -406,14 +406,14 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
                             left = 32u;
                         }
                         more = (word & 0xFu) == 0u;
-                        ln = *reinterpret_cast<const float4*>(len + s2);
+                        ln = *reinterpret_cast<const float4*>(&len[s2]);
                     }
                     float4 a;
                     a.x = adv = adv + l.x;
                     a.y = adv = adv + l.y;
                     a.z = adv = adv + l.z;
                     a.w = adv = adv + l.w;
-                    *reinterpret_cast<float4*>(w.adv + s) = a;
+                    *reinterpret_cast<float4*>(&w.adv[s]) = a;
                     s = s2;
                     if (!more) break;
                     l = ln;
