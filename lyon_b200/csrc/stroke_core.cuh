@@ -73,12 +73,16 @@ struct Views {
     LYC_HD uint32_t F(uint32_t s) const { return segfs[s]; }  // SEG_*_BIT flags in the top bits
     LYC_HD uint32_t SRC(uint32_t s) const { return seg_id[segfs[s] & SEG_MASK]; }
     LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
+    LYC_HD bool D(uint32_t s) const { return adv[s] != adv[s]; }  // dropped by the merge filter: NaN advancement
 };
 
 // The same slot arrays for ONE TILE of whole paths held in shared memory by the fused kernel (stroke_tile.cuh):
 // slot indices are tile-relative, flags are one byte (SEG_*_BIT >> 24), the endpoint id is stored per slot.
 static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08, TF_EVAL = 0x04, TF_CUBIC = 0x02,
                      TF_LAST = 0x01;
+// CTA tiles (TileViews) use two of the low bits for the merge filter: FLAGGED = the point MAY be within the merge distance of
+// its predecessor (written with the slot, never changed), DROPPED = the merge filter dropped it (tile_resolve_run).
+static const uint8_t TF_FLAGGED = 0x02, TF_DROPPED = 0x04;
 // One slot array of a CTA tile.  Under nvcc it is a 32-bit byte offset into the CTA's dynamic shared memory: the accessors
 // go through the `extern __shared__` symbol, so every access compiles to LDS / STS with 32-bit address arithmetic (a
 // pointer kept in a struct that is passed to out-of-line routines degrades to generic LD / ST with 64-bit address
@@ -141,6 +145,7 @@ struct TileViews {
     LYC_HD uint32_t F(uint32_t s) const { return (uint32_t)flags[s] << 24; }
     LYC_HD uint32_t SRC(uint32_t s) const { return src[s]; }
     LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
+    LYC_HD bool D(uint32_t s) const { return (flags[s] & TF_DROPPED) != 0; }  // dropped by the merge filter
     LYC_HD TArr<float> len() const { return voff.as<float>(); }
 };
 
@@ -842,7 +847,7 @@ LYC_NOINLINE void tessellate_round_cap_nl(Sink& sink, VertexTemplate vt, V2 cent
 // Slot neighbourhood helpers (W = Views or TileViews)
 // ---------------------------------------------------------------------------------------------------------
 template <class W>
-LYC_HD bool slot_dropped(const W& w, uint32_t s) { return is_nan(w.A(s)); }
+LYC_HD bool slot_dropped(const W& w, uint32_t s) { return w.D(s); }
 template <class W>
 LYC_HD uint32_t prev_kept(const W& w, uint32_t s) {  // s is a kept non-Begin point: a kept predecessor exists
     uint32_t j = s - 1u;

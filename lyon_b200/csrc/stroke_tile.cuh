@@ -257,11 +257,15 @@ LYC_HD void tile_gen_verb_full(const TileViews& w, const StrokeParams& p, uint8_
             pos = v;
         }
         const uint32_t s = s0 + k;
+        // |P - prev| and the "maybe mergeable" flag (point_gen_slot in stroke_core.cuh): a pair further apart than sqrt(5)x
+        // the merge distance can never be merged; NaN distances are flagged too
+        const V2 d = pos - prev;
+        const float d2 = sqlen(d);
         w.pos[s] = pos;
         w.t[s] = ts;
-        w.flags[s] = (uint8_t)(ts != 1.0f ? TF_FS : 0);
+        w.flags[s] = (uint8_t)((ts != 1.0f ? TF_FS : 0) | (!(d2 >= p.flag_thr) ? TF_FLAGGED : 0));
         w.src[s] = src;
-        w.len()[s] = tile_len_flagged(p, pos, prev);
+        w.len()[s] = sqrtf(d2);
         prev = pos;
     }
 }
@@ -471,6 +475,133 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
                 m++;
             }
         }
+        ++s;
+    }
+}
+
+// ---- the merge filter and the advancement chain of the CTA-tile kernel ------------------------------------------------
+// The merge filter of fixed_width_step_impl (stroke.rs:1530-1536) compares a point with the last KEPT point, which is
+// sequential -- but only inside a RUN of consecutive flagged points: an unflagged point is certainly kept (it is further
+// than sqrt(5)x the merge distance from its predecessor, which in turn is within the merge distance of whatever point
+// is the last kept one), so the point before a run is kept whatever happened earlier.  One thread resolves one run, all
+// runs of the tile at once (tile kernel: a thread per slot looks for run starts): a dropped point gets TF_DROPPED and the
+// length -0.0f (adv + -0.0f == adv: the advancement chain then needs no branch), a kept one the distance to the last kept
+// point; the unflagged point right after a dropped one is re-measured against the last kept point as the reference does
+// (last_kept != s - 1).  `s` must be a run start: flagged, its predecessor not flagged (an ordinary point or a Begin).
+template <class W>
+LYC_HD bool tile_run_start(const W& w, uint32_t s) {
+    const uint8_t fl = w.flags[s];
+    if (!(fl & TF_FLAGGED) || (fl & (TF_BEGIN | TF_END)) || s == 0u) return false;
+    return !(w.flags[s - 1u] & TF_FLAGGED);
+}
+template <class W>
+LYC_HD void tile_resolve_run(const W& w, const StrokeParams& p, uint32_t s, uint32_t n_slots) {
+    const auto len = w.len();
+    uint32_t last_kept = s - 1u;
+    bool prev_flagged = true;  // (of slot r - 1, for r > s)
+    for (uint32_t r = s; r < n_slots; ++r) {
+        const uint8_t fl = w.flags[r];
+        if (fl & (TF_BEGIN | TF_END)) break;
+        const bool flagged = (fl & TF_FLAGGED) != 0;
+        // the run goes on while flagged points follow each other, and through the point after a dropped one; a flagged
+        // point behind a kept unflagged one starts a run of its own (another thread's)
+        if (r != s && !((flagged && prev_flagged) || last_kept != r - 1u)) break;
+        const V2 pl = w.pos[last_kept], ps = w.pos[r];
+        if (sqlen(pl - ps) < p.merge_thr) {
+            w.flags[r] = (uint8_t)(fl | TF_DROPPED);
+            len[r] = -0.0f;
+        } else {
+            len[r] = length(ps - pl);
+            last_kept = r;
+        }
+        prev_flagged = flagged;
+    }
+}
+
+// The advancement chain of one path = slots [sa, sb) of the tile, after tile_resolve_run: adv += |edge| over every point of
+// a sub-path (stroke.rs:1546-1550, 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), and the
+// sub-path record of every End slot (begin slot, kept points capped at 3, may_need_empty_cap stroke.rs:1180, 1533, closed).
+// The chain itself is branch-free: 32 points per step on vector loads / stores (eight 16-byte loads, 32 dependent
+// additions, eight 16-byte stores), then 4, then 1.
+template <class W>
+LYC_HD void tile_path_chain(const W& w, const StrokeParams& p, uint32_t sa, uint32_t sb) {
+    (void)p;
+    const float nan = u2f(0x7FC00000u);
+    const auto len = w.len();
+    float carry = 0.0f;
+    uint32_t s = sa;
+    while (s < sb) {
+        uint8_t fl = w.flags[s];
+        const uint32_t begin_slot = s;
+        float adv = carry;
+        uint32_t m = 0u;
+        if (!(fl & TF_END)) {  // a Begin (a sub-path that starts with anything else is treated as if it had one)
+            w.adv[s] = adv;
+            m = 1u;
+            ++s;
+            // ---- the chain up to the End slot of the sub-path ----
+            while (s < sb) {
+#ifdef __CUDA_ARCH__
+                if ((s & 3u) == 0u && s + 32u < sb) {  // 32 slots, none of them a Begin / End?
+                    uint32_t any = 0u;  // (the flag bytes of a tile are 4-byte aligned, not more)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) any |= *reinterpret_cast<const uint32_t*>(&w.flags[s + 4 * q]);
+                    if (!(any & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
+                        float4 l[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(&len[s + 4 * q]);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            l[q].x = adv = adv + l[q].x;
+                            l[q].y = adv = adv + l[q].y;
+                            l[q].z = adv = adv + l[q].z;
+                            l[q].w = adv = adv + l[q].w;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&w.adv[s + 4 * q]) = l[q];
+                        s += 32u;
+                        continue;
+                    }
+                }
+                if ((s & 3u) == 0u && s + 4u < sb) {
+                    const uint32_t f4 = *reinterpret_cast<const uint32_t*>(&w.flags[s]);
+                    if (!(f4 & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
+                        float4 l = *reinterpret_cast<const float4*>(&len[s]);
+                        l.x = adv = adv + l.x;
+                        l.y = adv = adv + l.y;
+                        l.z = adv = adv + l.z;
+                        l.w = adv = adv + l.w;
+                        *reinterpret_cast<float4*>(&w.adv[s]) = l;
+                        s += 4u;
+                        continue;
+                    }
+                }
+#endif
+                fl = w.flags[s];
+                if (fl & (TF_BEGIN | TF_END)) break;
+                adv = adv + len[s];
+                w.adv[s] = adv;
+                ++s;
+            }
+            // kept points of the sub-path, capped at 3 (the chain does not count: dropped points are rare)
+            for (uint32_t r = begin_slot + 1u; r < s && m < 3u; ++r)
+                if (!(w.flags[r] & TF_DROPPED)) ++m;
+            if (s >= sb || !(fl & TF_END)) {  // no End slot (cannot happen for a well-formed path): next sub-path
+                carry = adv;
+                continue;
+            }
+        }
+        // ---- the End slot ----
+        const bool close = (fl & TF_CLOSE) != 0;
+        // may_need_empty_cap: a point was dropped while only the Begin point was kept, or close() on a single point
+        bool mnec = m >= 1u && begin_slot + 1u < s && (w.flags[begin_slot + 1u] & TF_DROPPED) != 0;
+        if (close && m == 1u) mnec = true;
+        V2 rec;
+        rec.x = u2f(begin_slot);
+        rec.y = u2f(m | (mnec ? REC_MNEC : 0u) | (close ? REC_CLOSE : 0u));
+        w.pos[s] = rec;
+        w.adv[s] = nan;
+        if (!(close && m > 2u) && m >= 2u) carry = adv;
         ++s;
     }
 }

@@ -59,6 +59,10 @@ struct WTileViews {
     }
     LYC_HD uint32_t SRC(uint32_t s) const { return vsrc[verb_of(s)]; }
     LYC_HD uint32_t VO(uint32_t s) const { return cbase_v[s >> 5] + (off[s] & 0xFFFFu); }
+    LYC_HD bool D(uint32_t s) const {
+        const float a = A(s);
+        return a != a;
+    }
     LYC_HD uint32_t TO(uint32_t s) const { return cbase_t[s >> 5] + (off[s] >> 16); }
     LYC_HD float T(uint32_t s) const;
 };
@@ -122,6 +126,10 @@ LYC_HD void tile_gen_split_slot(const TileViews& w, const StrokeParams& p, const
     const float t = wt_gen_split_slot(w, p, points, pt, s0, r, j);
     w.t[s0 + j] = t;
     w.src[s0 + j] = src;
+    // CTA tiles keep the "maybe mergeable" flag in the flag byte and the length unsigned (tile_resolve_run)
+    const float l = w.len()[s0 + j];
+    w.flags[s0 + j] = (uint8_t)((w.flags[s0 + j] & TF_FS) | (len_flagged(l) ? TF_FLAGGED : 0));
+    w.len()[s0 + j] = fabsf(l);
 }
 
 // One ordinary slot: slot k of `cnt` of a verb of kind `kind` whose first stored point is `pt`.  Writes pos and flags;
@@ -308,6 +316,10 @@ struct EndRecView {
     LYC_HD uint32_t SRC(uint32_t s) const { return s == 0u ? r->src0 : r->src5; }
     LYC_HD uint32_t F(uint32_t s) const { return s < 6u ? (uint32_t)r->f[s] << 24 : (uint32_t)TF_END << 24; }
     LYC_HD uint32_t VO(uint32_t s) const { return s == 1u ? r->vo1 : r->vo4; }
+    LYC_HD bool D(uint32_t s) const {
+        const float a = A(s);
+        return a != a;
+    }
 };
 
 }  // namespace lyc

@@ -183,21 +183,14 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         }
         tile_gen_verb_full(w, p, verb, points, seg_pt[v], plans[v].n_a, seg_off[v], id);
     }
-    // phase 1c: special mask (phase 1a leaves the slots complete)
-    std::vector<uint32_t> special(NS / 32 + 2, 0);
-    for (uint32_t s = 0; s < NS; ++s)
-        if (tile_slot_special(w, s)) special[s >> 5] |= 1u << (s & 31u);
-    // phase 1d: flagged slots that are ordinary kept points after all.  Every other candidate is resolved in a first
-    // sweep and the rest in a second one, so both "neighbour already resolved" and "neighbour still flagged" occur
-    // (on the device the order is arbitrary).
+    // phase 1c: the merge filter, run by run (on the device all runs at once, in any order: here odd starts first)
     for (uint32_t pass = 0; pass < 2u; ++pass)
         for (uint32_t s = 0; s < NS; ++s)
-            if (((special[s >> 5] >> (s & 31u)) & 1u) && ((s & 1u) == pass) && tile_resolve_flagged(w, p, s))
-                special[s >> 5] &= ~(1u << (s & 31u));
+            if ((s & 1u) != pass && tile_run_start(w, s)) tile_resolve_run(w, p, s, NS);
     // phase 2: per path
     for (uint32_t path = 0; path < b->n_paths; ++path) {
         uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
-        tile_path_walk(w, p, seg_off[vb], seg_off[ve], special.data());
+        tile_path_chain(w, p, seg_off[vb], seg_off[ve]);
     }
     // phase 3: classify + count
     std::vector<uint32_t> cnt_v(NS + 1, 0), cnt_t(NS + 1, 0);
