@@ -70,7 +70,7 @@ typedef struct {
  * ceil(num_attributes/2) attribute slots], and N+1 begin offsets per path (in verbs / in points). */
 typedef struct {
     const uint8_t* verbs;
-    const float* points;
+    const float* points; /* 8-byte aligned */
     const uint32_t* path_verb_begin;
     const uint32_t* path_point_begin;
     uint32_t n_paths;

@@ -24,7 +24,9 @@
 
 namespace lyc {
 
-struct V2 {
+// 8-byte aligned: one 64-bit load / store per point (LDS.64 / LDG.64); every point array handed to the library is at least
+// 8-byte aligned (the C entry points check).
+struct alignas(8) V2 {
     float x, y;
 };
 LYC_HD V2 v2(float x, float y) { return V2{x, y}; }

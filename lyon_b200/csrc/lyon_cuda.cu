@@ -103,17 +103,18 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t 
 // predecessor are loaded in the same round trip.  Each array keeps its own state (a predecessor's two descriptors are
 // two stores and may be observed in different states).  Called by all 32 lanes of ONE warp.
 __device__ __forceinline__ void lookback_exclusive_pair(uint64_t* desc_a, uint64_t* desc_b, uint32_t tile, uint64_t agg_a,
-                                                        uint64_t agg_b, uint64_t* excl_a, uint64_t* excl_b) {
+                                                        uint64_t agg_b, uint64_t* excl_a, uint64_t* excl_b,
+                                                        bool published = false) {
     const unsigned lane = threadIdx.x & 31u;
     if (tile == 0u) {
-        if (lane == 0u) {
+        if (lane == 0u && !published) {
             st_desc(&desc_a[0], ST_PREFIX | agg_a);
             st_desc(&desc_b[0], ST_PREFIX | agg_b);
         }
         *excl_a = *excl_b = 0ull;
         return;
     }
-    if (lane == 0u) {
+    if (lane == 0u && !published) {
         st_desc(&desc_a[tile], ST_AGG | agg_a);
         st_desc(&desc_b[tile], ST_AGG | agg_b);
     }
@@ -1178,6 +1179,7 @@ template <int NPTS>
 int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, const uint64_t* d_offsets, uint64_t total,
                  float* d_points, float* d_t) {
     if (!c || (n && (!d_ctrl || !d_offsets)) || (total && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_points) | reinterpret_cast<uintptr_t>(d_ctrl)) & 7u) return LYON_ERR_INVALID_ARGUMENT;
     if (n == 0 || total == 0) return LYON_OK;
     const size_t smem = sizeof(FlatSmem<NPTS>);
     CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
@@ -1192,6 +1194,7 @@ template <int NPTS>
 int flatten_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets, float* d_points,
                   uint64_t capacity, float* d_t, uint64_t* total) {
     if (!c || !total || (n && (!d_ctrl || !d_offsets)) || (capacity && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_points) | reinterpret_cast<uintptr_t>(d_ctrl)) & 7u) return LYON_ERR_INVALID_ARGUMENT;
     if (!(tol > 0.0f)) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN / non-positive
     *total = 0;
     if (n == 0) {
@@ -1599,6 +1602,7 @@ int vw_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_option
         return LYON_OK;
     }
     if (!b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(b->points) & 7u) return LYON_ERR_INVALID_ARGUMENT;  // points are read as 64-bit pairs
     const uint32_t np = b->n_paths;
     TRY(ensure(c, c->vw_nv, ((size_t)np + 1) * 4));
     TRY(ensure(c, c->vw_nt, ((size_t)np + 1) * 4));
@@ -1763,6 +1767,7 @@ int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, fl
         return LYON_OK;
     }
     if (!b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(b->points) & 7u) return LYON_ERR_INVALID_ARGUMENT;  // points are read as 64-bit pairs
     const uint32_t np = b->n_paths;
     TRY(ensure(c, c->pf_rec, ((size_t)b->n_verbs + 1) * sizeof(PfRec)));
     TRY(ensure(c, c->vw_nv, ((size_t)np + 1) * 4));
@@ -1851,6 +1856,7 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
         return LYON_OK;
     }
     if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(b->points) & 7u) return LYON_ERR_INVALID_ARGUMENT;  // points are read as 64-bit pairs
     c->tile_planned = false;
     {
         bool usable = false;
@@ -2104,6 +2110,7 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyo
     const bool vw = o->variable_line_width >= 0 && b->num_attributes > 0;  // thread-per-path kernels: plan, then emit
     if (!vw && b->n_paths && b->n_verbs) {
         if (!b->verbs || !b->points || !b->path_verb_begin) return LYON_ERR_INVALID_ARGUMENT;
+        if (reinterpret_cast<uintptr_t>(b->points) & 7u) return LYON_ERR_INVALID_ARGUMENT;  // points are read as 64-bit pairs
         c->params = make_params(*o, b->num_attributes);
         TRY(tile_prepass(c, b, &usable));
     }

@@ -538,6 +538,26 @@ LYC_HD uint8_t join_encode(const Join& j) {
     return (uint8_t)((j.fast ? JC_FAST : 0) | (j.fold[SIDE_POSITIVE] ? JC_FOLD_POS : 0) | (j.fold[SIDE_NEGATIVE] ? JC_FOLD_NEG : 0) |
                      (j.has_single[SIDE_POSITIVE] ? JC_SINGLE_POS : 0) | (j.has_single[SIDE_NEGATIVE] ? JC_SINGLE_NEG : 0));
 }
+// The CTA-tile kernels keep a shorter code: all the NEXT slot's edge triangles need of this join are the two vertices the
+// edge leaves from (add_edge_triangles' p0_neg / p0_pos with the fold remaps applied), as offsets 0..3 from the join's first
+// vertex: bit 0 JC_FAST, bits 1-2 the Negative-side exit vertex, bits 3-4 the Positive-side one.  `j` carries ids relative to 0.
+static const uint8_t JX_FAST = (uint8_t)(JC_FAST | (1u << 1) | (0u << 3));  // flattened_step: Positive = 0, Negative = 1
+LYC_HD uint8_t join_exit_code(const Join& j) {
+    const uint32_t en = j.fold[SIDE_POSITIVE] ? j.prev_v[SIDE_POSITIVE] : j.next_v[SIDE_NEGATIVE];
+    const uint32_t ep = j.fold[SIDE_NEGATIVE] ? j.prev_v[SIDE_NEGATIVE] : j.next_v[SIDE_POSITIVE];
+    return (uint8_t)((j.fast ? JC_FAST : 0) | ((en & 3u) << 1) | ((ep & 3u) << 3));
+}
+// add_edge_triangles (stroke.rs:1869-1904) from an exit code: for a fixed line width the vertices of two joins are all
+// distinct, so both triangles are always there.
+template <class Sink>
+LYC_HD void add_edge_triangles_x(Sink& sink, uint32_t p0_base, uint8_t p0_code, const Join& b) {
+    const uint32_t p0_neg = p0_base + ((p0_code >> 1) & 3u), p0_pos = p0_base + ((p0_code >> 3) & 3u);
+    uint32_t p1_neg = b.prev_v[SIDE_NEGATIVE], p1_pos = b.prev_v[SIDE_POSITIVE];
+    if (b.fold[SIDE_POSITIVE]) p1_neg = b.next_v[SIDE_POSITIVE];
+    if (b.fold[SIDE_NEGATIVE]) p1_pos = b.next_v[SIDE_NEGATIVE];
+    sink.add_triangle(p0_neg, p0_pos, p1_pos);
+    sink.add_triangle(p0_neg, p1_pos, p1_neg);
+}
 LYC_HD void join_decode_ids(Join& j, uint8_t code, uint32_t base) {  // fills only what add_edge_triangles reads
     j.fast = (code & JC_FAST) != 0;
     j.fold[SIDE_POSITIVE] = (code & JC_FOLD_POS) != 0;
@@ -934,7 +954,7 @@ LYC_HD SlotClass classify_slot(const W& w, uint32_t s) {
     return c;
 }
 // Count pass of a join that does not take the flattened_step fast path.
-template <class W>
+template <bool XC = false, class W>
 LYC_HD void count_full_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t* nv,
                             uint32_t* nt, uint8_t* code) {
     Join j;
@@ -953,7 +973,7 @@ LYC_HD void count_full_join(const W& w, const StrokeParams& o, uint32_t s, uint3
     tessellate_join(sink, vt, j, o);
     *nv = sink.nv;
     *nt = sink.nt;
-    *code = join_encode(j);
+    *code = XC ? join_exit_code(j) : join_encode(j);
 }
 // Emit pass of a fast join (flattened_step, stroke.rs:1743-1806).
 template <class Sink, class W, class JC>
@@ -973,14 +993,17 @@ LYC_HD void emit_fast_join(const W& w, const StrokeParams& o, uint32_t s, uint32
     }
 }
 // Emit pass of any other stream join.
-template <class Sink, class W, class JC>
+template <bool XC = false, class Sink, class W, class JC>
 LYC_HD void emit_full_join(const W& w, const StrokeParams& o, uint32_t s, uint32_t pk, uint32_t nk, uint32_t global_base,
                            JC jcode, Sink& sink) {
     Join j;
     stream_join(w, o, s, pk, nk, j);
     VertexTemplate vt = slot_vertex_template(w, o, s);
     emit_join_vertices(sink, vt, j);
-    if (!(w.F(pk) & SEG_BEGIN_BIT)) edge_to_previous_join(w, o, s, pk, global_base, jcode, j, sink);
+    if (!(w.F(pk) & SEG_BEGIN_BIT)) {
+        if (XC) add_edge_triangles_x(sink, global_base + w.VO(pk), jcode[pk], j);
+        else edge_to_previous_join(w, o, s, pk, global_base, jcode, j, sink);
+    }
     tessellate_join(sink, vt, j, o);
 }
 
