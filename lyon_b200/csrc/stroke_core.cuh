@@ -135,7 +135,7 @@ struct TileViews {
     TArr<float> adv;
     TArr<uint32_t> src;   // EndpointId of the slot's vertex source
     TArr<uint8_t> flags;  // TF_*
-    TArr<uint32_t> voff;  // aliased by `len` until the count phase
+    TArr<uint32_t> voff;
     TArr<uint32_t> toff;
     TArr<uint8_t> jcode;
     uint32_t n_slots;
@@ -146,7 +146,7 @@ struct TileViews {
     LYC_HD uint32_t SRC(uint32_t s) const { return src[s]; }
     LYC_HD uint32_t VO(uint32_t s) const { return voff[s]; }
     LYC_HD bool D(uint32_t s) const { return (flags[s] & TF_DROPPED) != 0; }  // dropped by the merge filter
-    LYC_HD TArr<float> len() const { return voff.as<float>(); }
+    LYC_HD TArr<float> len() const { return adv; }  // |P - prev| until the advancement chain turns it into adv, in place
 };
 
 LYC_HD uint32_t verb_point_count(uint8_t verb, uint32_t a) {

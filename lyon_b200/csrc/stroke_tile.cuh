@@ -199,12 +199,15 @@ LYC_HD void tile_gen_verb(const TileViews& w, const StrokeParams& p, uint8_t ver
 // polynomial and re-loads the control points for every point, four times the instructions.  Split quadratics are not
 // handled here (tile_gen_split_slot).  `n` = the verb's Wang count (pre-pass).
 LYC_HD void tile_gen_verb_full(const TileViews& w, const StrokeParams& p, uint8_t verb, const V2* points, uint32_t pt, float n,
-                               uint32_t s0, uint32_t src) {
+                               uint32_t s0, uint32_t src, uint32_t begin_slot = 0u) {
     if (verb == VERB_END || verb == VERB_CLOSE) {
         w.t[s0] = 1.0f;
         w.flags[s0] = (uint8_t)(TF_END | (verb == VERB_CLOSE ? TF_CLOSE : 0));
         w.src[s0] = src;
-        w.len()[s0] = 0.0f;  // pos / adv: the sub-path record, written by the walk
+        w.len()[s0] = 0.0f;
+        // the sub-path record: the Begin slot now, the kept-point count and may_need_empty_cap once the merge filter has
+        // run (tile_end_record_finish)
+        w.pos[s0] = v2(u2f(begin_slot), u2f(verb == VERB_CLOSE ? REC_CLOSE : 0u));
         return;
     }
     const bool curve = verb == VERB_QUAD || verb == VERB_CUBIC, cubic = verb == VERB_CUBIC;
@@ -518,90 +521,89 @@ LYC_HD void tile_resolve_run(const W& w, const StrokeParams& p, uint32_t s, uint
     }
 }
 
-// The advancement chain of one path = slots [sa, sb) of the tile, after tile_resolve_run: adv += |edge| over every point of
-// a sub-path (stroke.rs:1546-1550, 1657-1661, 1759-1769, 2140) with the open-sub-path carry (stroke.rs:1359), and the
-// sub-path record of every End slot (begin slot, kept points capped at 3, may_need_empty_cap stroke.rs:1180, 1533, closed).
-// The chain itself is branch-free: 32 points per step on vector loads / stores (eight 16-byte loads, 32 dependent
-// additions, eight 16-byte stores), then 4, then 1.
+// The sub-path record of End slot `e` (written by the verb phase with the Begin slot and the closed bit) gets what depends on
+// the merge filter: the number of kept points capped at 3, and may_need_empty_cap (stroke.rs:1180, 1533: a point was dropped
+// while only the Begin point was kept -- i.e. the point after the Begin was dropped -- or close() on a single point).
+template <class W>
+LYC_HD void tile_end_record_finish(const W& w, uint32_t e) {
+    V2 rec = w.pos[e];
+    const uint32_t b0 = f2u(rec.x);
+    const bool close = (f2u(rec.y) & REC_CLOSE) != 0u;
+    uint32_t m = (b0 < e && (w.flags[b0] & TF_BEGIN)) ? 1u : 0u;
+    for (uint32_t r = b0 + 1u; r < e && m < 3u && m >= 1u; ++r)
+        if (!(w.flags[r] & (TF_DROPPED | TF_BEGIN | TF_END))) ++m;
+    bool mnec = m >= 1u && b0 + 1u < e && (w.flags[b0 + 1u] & TF_DROPPED) != 0;
+    if (close && m == 1u) mnec = true;
+    rec.y = u2f(m | (mnec ? REC_MNEC : 0u) | (close ? REC_CLOSE : 0u));
+    w.pos[e] = rec;
+}
+
+// The advancement chain of one path = slots [sa, sb) of the tile, after tile_resolve_run and tile_end_record_finish:
+// adv += |edge| over every point of a sub-path (stroke.rs:1546-1550, 1657-1661, 1759-1769, 2140) with the open-sub-path
+// carry (stroke.rs:1359).  In place: the slot's length becomes its advancement.  The chain itself is branch-free: 32 points
+// per step on vector loads / stores (eight 16-byte loads, 32 dependent additions, eight 16-byte stores), then 4, then 1.
+// Nothing that decides vertex or triangle COUNTS depends on it, so the tile kernel runs it after its counts are published.
 template <class W>
 LYC_HD void tile_path_chain(const W& w, const StrokeParams& p, uint32_t sa, uint32_t sb) {
     (void)p;
     const float nan = u2f(0x7FC00000u);
     const auto len = w.len();
-    float carry = 0.0f;
+    float carry = 0.0f, adv = 0.0f;
     uint32_t s = sa;
     while (s < sb) {
-        uint8_t fl = w.flags[s];
-        const uint32_t begin_slot = s;
-        float adv = carry;
-        uint32_t m = 0u;
-        if (!(fl & TF_END)) {  // a Begin (a sub-path that starts with anything else is treated as if it had one)
-            w.adv[s] = adv;
-            m = 1u;
+        const uint8_t fl = w.flags[s];
+        if (fl & TF_END) {
+            const uint32_t r = f2u(w.pos[s].y), m = r & 3u;
+            const bool close = (r & REC_CLOSE) != 0u;
+            w.adv[s] = nan;
+            if (!(close && m > 2u) && m >= 2u) carry = adv;
             ++s;
-            // ---- the chain up to the End slot of the sub-path ----
-            while (s < sb) {
+            continue;
+        }
+        if (fl & TF_BEGIN) {
+            adv = carry;
+            w.adv[s] = adv;
+            ++s;
+            continue;
+        }
 #ifdef __CUDA_ARCH__
-                if ((s & 3u) == 0u && s + 32u < sb) {  // 32 slots, none of them a Begin / End?
-                    uint32_t any = 0u;  // (the flag bytes of a tile are 4-byte aligned, not more)
+        if ((s & 3u) == 0u && s + 32u < sb) {  // 32 slots, none of them a Begin / End?
+            uint32_t any = 0u;                 // (the flag bytes of a tile are 4-byte aligned, not more)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) any |= *reinterpret_cast<const uint32_t*>(&w.flags[s + 4 * q]);
-                    if (!(any & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
-                        float4 l[8];
+            for (int q = 0; q < 8; ++q) any |= *reinterpret_cast<const uint32_t*>(&w.flags[s + 4 * q]);
+            if (!(any & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
+                float4 l[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(&len[s + 4 * q]);
+                for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(&len[s + 4 * q]);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            l[q].x = adv = adv + l[q].x;
-                            l[q].y = adv = adv + l[q].y;
-                            l[q].z = adv = adv + l[q].z;
-                            l[q].w = adv = adv + l[q].w;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&w.adv[s + 4 * q]) = l[q];
-                        s += 32u;
-                        continue;
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    l[q].x = adv = adv + l[q].x;
+                    l[q].y = adv = adv + l[q].y;
+                    l[q].z = adv = adv + l[q].z;
+                    l[q].w = adv = adv + l[q].w;
                 }
-                if ((s & 3u) == 0u && s + 4u < sb) {
-                    const uint32_t f4 = *reinterpret_cast<const uint32_t*>(&w.flags[s]);
-                    if (!(f4 & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
-                        float4 l = *reinterpret_cast<const float4*>(&len[s]);
-                        l.x = adv = adv + l.x;
-                        l.y = adv = adv + l.y;
-                        l.z = adv = adv + l.z;
-                        l.w = adv = adv + l.w;
-                        *reinterpret_cast<float4*>(&w.adv[s]) = l;
-                        s += 4u;
-                        continue;
-                    }
-                }
-#endif
-                fl = w.flags[s];
-                if (fl & (TF_BEGIN | TF_END)) break;
-                adv = adv + len[s];
-                w.adv[s] = adv;
-                ++s;
-            }
-            // kept points of the sub-path, capped at 3 (the chain does not count: dropped points are rare)
-            for (uint32_t r = begin_slot + 1u; r < s && m < 3u; ++r)
-                if (!(w.flags[r] & TF_DROPPED)) ++m;
-            if (s >= sb || !(fl & TF_END)) {  // no End slot (cannot happen for a well-formed path): next sub-path
-                carry = adv;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&w.adv[s + 4 * q]) = l[q];
+                s += 32u;
                 continue;
             }
         }
-        // ---- the End slot ----
-        const bool close = (fl & TF_CLOSE) != 0;
-        // may_need_empty_cap: a point was dropped while only the Begin point was kept, or close() on a single point
-        bool mnec = m >= 1u && begin_slot + 1u < s && (w.flags[begin_slot + 1u] & TF_DROPPED) != 0;
-        if (close && m == 1u) mnec = true;
-        V2 rec;
-        rec.x = u2f(begin_slot);
-        rec.y = u2f(m | (mnec ? REC_MNEC : 0u) | (close ? REC_CLOSE : 0u));
-        w.pos[s] = rec;
-        w.adv[s] = nan;
-        if (!(close && m > 2u) && m >= 2u) carry = adv;
+        if ((s & 3u) == 0u && s + 4u < sb) {
+            const uint32_t f4 = *reinterpret_cast<const uint32_t*>(&w.flags[s]);
+            if (!(f4 & (0x01010101u * (uint32_t)(TF_BEGIN | TF_END)))) {
+                float4 l = *reinterpret_cast<const float4*>(&len[s]);
+                l.x = adv = adv + l.x;
+                l.y = adv = adv + l.y;
+                l.z = adv = adv + l.z;
+                l.w = adv = adv + l.w;
+                *reinterpret_cast<float4*>(&w.adv[s]) = l;
+                s += 4u;
+                continue;
+            }
+        }
+#endif
+        adv = adv + len[s];
+        w.adv[s] = adv;
         ++s;
     }
 }

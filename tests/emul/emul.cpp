@@ -171,27 +171,25 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         for (uint32_t v = b->path_verb_begin[path]; v < b->path_verb_begin[path + 1]; ++v) verb_path[v] = path;
     for (uint32_t v = 0; v < NV; ++v)
         evt_before[v + 1] = evt_before[v] + ((b->verbs[v] != VERB_END && b->verbs[v] != VERB_CLOSE) ? 1u : 0u);
+    uint32_t begin_slot = 0u;
     for (uint32_t v = 0; v < NV; ++v) {
         uint8_t verb = b->verbs[v];
         uint32_t ncurve = verb == VERB_QUAD ? 2u : (verb == VERB_CUBIC ? 3u : 1u);
         uint32_t vb = b->path_verb_begin[verb_path[v]];
+        if (v == vb) begin_slot = seg_off[v];
         uint32_t id = p.num_attributes > 0 ? (seg_pt[v] - seg_pt[vb]) + ncurve - 1u : evt_before[v] - evt_before[vb];
         if (verb == VERB_QUAD && plans[v].tsplit >= 0.0f) {  // split quadratic: a lane per slot from the pre-pass's plan
             const SplitRec rec{plans[v].tsplit, plans[v].n_a, plans[v].n_b, 0.0f};
             for (uint32_t j = 0; j < plans[v].nslots; ++j) tile_gen_split_slot(w, p, points, seg_pt[v], seg_off[v], id, rec, j);
             continue;
         }
-        tile_gen_verb_full(w, p, verb, points, seg_pt[v], plans[v].n_a, seg_off[v], id);
+        if (verb == VERB_BEGIN) begin_slot = seg_off[v];
+        tile_gen_verb_full(w, p, verb, points, seg_pt[v], plans[v].n_a, seg_off[v], id, begin_slot);
     }
     // phase 1c: the merge filter, run by run (on the device all runs at once, in any order: here odd starts first)
     for (uint32_t pass = 0; pass < 2u; ++pass)
         for (uint32_t s = 0; s < NS; ++s)
             if ((s & 1u) != pass && tile_run_start(w, s)) tile_resolve_run(w, p, s, NS);
-    // phase 2: per path
-    for (uint32_t path = 0; path < b->n_paths; ++path) {
-        uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
-        tile_path_chain(w, p, seg_off[vb], seg_off[ve]);
-    }
     // phase 3: classify + count
     std::vector<uint32_t> cnt_v(NS + 1, 0), cnt_t(NS + 1, 0);
     for (uint32_t s = 0; s < NS; ++s) {
@@ -207,6 +205,7 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
                 count_full_join(w, p, s, c.pk, c.nk, &nv, &nt, &code);
             }
         } else if (c.kind == KIND_END) {
+            tile_end_record_finish(w, s);
             end_slot_count(w, p, s, &nv, &nt);
             uint32_t gv, gt;
             end_slot_count_generic(w, p, s, &gv, &gt);
@@ -217,7 +216,7 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
         jcode[s] = code;
     }
     uint64_t tv = 0, tt = 0;
-    for (uint32_t s = 0; s < NS; ++s) {  // voff aliases len: only overwritten after phase 2
+    for (uint32_t s = 0; s < NS; ++s) {
         voff[s] = (uint32_t)tv;
         toff[s] = (uint32_t)tt;
         tv += cnt_v[s];
@@ -227,6 +226,11 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     toff[NS] = (uint32_t)tt;
     if (tv > 0xFFFFFFFFull || tt > 0xFFFFFFFFull) return LYON_ERR_TOO_MANY_VERTICES;
     if (tv && vertex_base + tv - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
+    // phase 2 (no count depends on it; the kernel runs it while the look-back waits): advancement chain, per path
+    for (uint32_t path = 0; path < b->n_paths; ++path) {
+        uint32_t vb = b->path_verb_begin[path], ve = b->path_verb_begin[path + 1];
+        tile_path_chain(w, p, seg_off[vb], seg_off[ve]);
+    }
     // phase 4: emit
     GpuVertex* V = (GpuVertex*)malloc((tv ? tv : 1) * sizeof(GpuVertex));
     uint32_t* I = (uint32_t*)malloc((tt ? tt : 1) * 12);
