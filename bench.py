@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flatten", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -220,6 +220,10 @@ def main():
     tz = DeviceTessellator(local_rank)
     dbatch = tz.upload(batch)
     torch.cuda.synchronize()
+    if world > 1:  # the library's own communicator: rank 0 creates the NCCL id, torch.distributed only carries it
+        ids = [tz.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        tz.comm_init(ids[0], rank, world)
 
     verts = idx = None
     tz.enable_timing(True)
@@ -236,10 +240,10 @@ def main():
             v, i = tz.stroke_fused(dbatch, opts)
             nv, ni = int(v.shape[0]), int(i.shape[0])
         else:
-            v, i = tz.stroke_fused(dbatch, opts)  # local ids
+            # lyon_cuda_stroke_fused_sharded: local ids, then the one collective (ncclAllGather of {V_r, I_r, status} on the
+            # context's stream) and the index rebase with the base read on the device -- no host hop between the three
+            v, i, _base, _tot = tz.stroke_fused_sharded(dbatch, opts)
             nv, ni = int(v.shape[0]), int(i.shape[0])
-            base, _ibase, _tot = exchange_totals(nv, ni, device=dev)  # the one collective: 16 B per rank over NCCL
-            tz.rebase_indices(i, nv, base)  # global ids: one streaming pass over this rank's indices
         if ev:
             ev[1].record()
         if record:
@@ -298,7 +302,8 @@ def main():
         verts = idx = None
         tz._own_v = tz._own_i = None
         torch.cuda.empty_cache()
-        pipe = HostPipeline(local_rank, chunk_paths=25000)
+        # >= 16 chunks per rank, so that the two alternating streams reach their steady state at every N
+        pipe = HostPipeline(local_rank, chunk_paths=max(4096, min(25000, (batch.n_paths + 15) // 16)))
         pipe.stage(batch)
         pipe.run(opts)  # warm-up: sizes + pins the output arrays
         barrier()
@@ -310,8 +315,9 @@ def main():
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         e2e = {"value": sum_over_ranks(ev) / e2e_s, "unit": "vertices/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-               "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_s * 1e3, "api": "HostPipeline.run (chunked "
-               "tessellate_paths: pinned host inputs -> H2D -> plan/emit -> D2H of every vertex and index)"}
+               "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_s * 1e3, "api": "lyon_cuda_tessellate_paths_into (C ABI; "
+               "pinned host inputs -> chunked H2D -> fused stroke kernels -> D2H of every vertex and index, two streams)",
+               "chunk_paths": pipe.chunk_paths}
         del pipe
         torch.cuda.empty_cache()
 

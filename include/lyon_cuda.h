@@ -194,6 +194,46 @@ int lyon_cuda_tessellate_paths(lyon_cuda_ctx* ctx, const lyon_path_batch* h_batc
                                uint64_t* n_vertices, uint32_t** h_indices, uint64_t* n_indices);
 void lyon_cuda_free_host(void* p);
 
+/* The same call for production use: caller-provided host buffers (reused across calls like bench/tess reuses its
+ * VertexBuffers, bench/tess/src/main.rs:186-196; pinned memory from lyon_cuda_host_alloc makes the copies asynchronous),
+ * the batch cut into chunks of `chunk_paths` whole paths (0 = 32768) that are uploaded, tessellated and downloaded on two
+ * alternating streams, so the download of one chunk overlaps the upload and the kernels of the next.  Chunk c is emitted
+ * with vertex_base = the vertices of the chunks before it: the concatenated buffers equal the result of one
+ * StrokeTessellator::tessellate_path loop over one VertexBuffers (stroke.rs:164-177, geometry_builder.rs:325-349).
+ * Capacities are in vertices / in u32 indices.  *n_vertices / *n_indices always receive the exact sizes; when a capacity
+ * is too small the whole batch is still counted and LYON_ERR_BUFFER_TOO_SMALL is returned (grow and call again).
+ * Needs h_batch->path_point_begin. */
+int lyon_cuda_tessellate_paths_into(lyon_cuda_ctx* ctx, const lyon_path_batch* h_batch, const lyon_stroke_options* options,
+                                    lyon_stroke_vertex* h_vertices, uint64_t vertex_capacity, uint32_t* h_indices,
+                                    uint64_t index_capacity, uint32_t chunk_paths, uint64_t* n_vertices, uint64_t* n_indices);
+/* Page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost). */
+int lyon_cuda_host_alloc(void** p, size_t bytes);
+void lyon_cuda_host_free(void* p);
+
+/* ---- multi-GPU: one process (or thread) per GPU, one context each ------------------------------------------------
+ * Paths are independent (a fresh StrokeBuilderImpl per tessellate call, stroke.rs:133-134), so the batch is cut into
+ * nranks contiguous path ranges and every rank strokes its own.  The only exchange is an all-gather of the per-rank
+ * totals {V_r, I_r} over NCCL; rank r's indices are rebased by sum(V_q, q < r) (BuffersBuilder::with_vertex_offset,
+ * geometry_builder.rs:325-329), so the concatenation of the per-rank buffers is the single-GPU result bit for bit.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", or the path in $LYON_NCCL_LIB). */
+#define LYON_CUDA_COMM_ID_BYTES 128
+/* Rank 0 creates the 128-byte id (ncclGetUniqueId) and the application hands it to every rank. */
+int lyon_cuda_comm_unique_id(uint8_t* id128);
+/* Collective: every rank calls it with the same id (ncclCommInitRank on the context's device). */
+int lyon_cuda_comm_init(lyon_cuda_ctx* ctx, const uint8_t* id128, int rank, int nranks);
+int lyon_cuda_comm_destroy(lyon_cuda_ctx* ctx);
+/* Collective: lyon_cuda_stroke_fused on this rank's slice `d_batch` with slice-local ids, the all-gather on the context's
+ * stream straight behind the kernels, then the index rebase with the base read from the gathered totals on the device
+ * (no host round trip in between).  *vertex_base receives sum(V_q, q < rank); h_totals (may be NULL) receives
+ * {V_q, I_q} for q = 0 .. nranks-1 (2 * nranks u64).  A rank whose slice fails still takes part in the exchange: it
+ * returns its own error, the other ranks return LYON_ERR_INTERNAL naming it (LYON_ERR_BUFFER_TOO_SMALL on every rank when
+ * a rank's buffers were too small: all ranks call again).  LYON_ERR_TOO_MANY_VERTICES when the job
+ * as a whole emits more than u32::MAX vertices (geometry_builder.rs:578-581). */
+int lyon_cuda_stroke_fused_sharded(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, const lyon_stroke_options* options,
+                                   lyon_stroke_vertex* d_vertices, uint64_t vertex_capacity, uint32_t* d_indices,
+                                   uint64_t index_capacity, uint64_t* d_path_vertex_end, uint64_t* d_path_index_end,
+                                   uint64_t* n_vertices, uint64_t* n_indices, uint64_t* vertex_base, uint64_t* h_totals);
+
 #ifdef __cplusplus
 }
 #endif

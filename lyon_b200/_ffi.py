@@ -34,6 +34,8 @@ SYMBOLS = [
     "lyon_cuda_interpolate_attributes",
     "lyon_cuda_enable_timing", "lyon_cuda_last_kernel_ms",
     "lyon_cuda_tessellate_paths", "lyon_cuda_free_host",
+    "lyon_cuda_tessellate_paths_into", "lyon_cuda_host_alloc", "lyon_cuda_host_free",
+    "lyon_cuda_comm_unique_id", "lyon_cuda_comm_init", "lyon_cuda_comm_destroy", "lyon_cuda_stroke_fused_sharded",
 ]
 
 
@@ -99,5 +101,15 @@ def lib():
                                              ctypes.POINTER(vp), pu64, ctypes.POINTER(vp), pu64]
     L.lyon_cuda_free_host.argtypes = [vp]
     L.lyon_cuda_free_host.restype = None
+    L.lyon_cuda_tessellate_paths_into.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), vp, u64, vp, u64,
+                                                  u32, pu64, pu64]
+    L.lyon_cuda_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.lyon_cuda_host_free.argtypes = [vp]
+    L.lyon_cuda_host_free.restype = None
+    L.lyon_cuda_comm_unique_id.argtypes = [vp]
+    L.lyon_cuda_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.lyon_cuda_comm_destroy.argtypes = [vp]
+    L.lyon_cuda_stroke_fused_sharded.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), vp, u64, vp, u64,
+                                                 vp, vp, pu64, pu64, pu64, pu64]
     _LIB = L
     return L

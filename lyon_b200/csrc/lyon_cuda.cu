@@ -1088,7 +1088,11 @@ struct lyon_cuda_ctx {
     uint32_t n_paths = 0;
     uint64_t n_vertices = 0, n_triangles = 0;
     size_t ws_bytes = 0;
+    struct HostPipe* host_pipe = nullptr;  // lyon_cuda_tessellate_paths_into (host_pipeline.cuh)
+    struct CommState* comm = nullptr;      // lyon_cuda_comm_init (sharded.cuh)
 };
+static void host_pipe_destroy(struct HostPipe* hp);
+static void comm_state_destroy(struct CommState* s);
 
 namespace {
 
@@ -1664,6 +1668,30 @@ int vw_emit(lyon_cuda_ctx* c, GpuVertex* d_vertices, uint32_t* d_indices, uint64
 // ---------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------
+// Every entry point runs on the context's device whatever device is current in the calling thread, and leaves the
+// caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// The two-phase entry points (stroke plan -> emit, flatten_paths count -> emit) keep their plan in workspace that the
+// other pipelines reuse (tickets, descriptors, count / offset buffers).  Any call that may overwrite that workspace
+// drops the plans it does not own, so a stale emit fails with LYON_ERR_INVALID_ARGUMENT instead of reading another
+// pipeline's data.
+enum { KEEP_NONE = 0, KEEP_STROKE = 1, KEEP_PATH_FLATTEN = 2 };
+static void drop_plans(lyon_cuda_ctx* c, int keep) {
+    if (!(keep & KEEP_STROKE)) c->planned = c->tile_planned = c->vw_planned = false;
+    if (!(keep & KEEP_PATH_FLATTEN)) c->pf_planned = false;
+}
+
 extern "C" {
 
 int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
@@ -1671,7 +1699,9 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LYON_ERR_CUDA;
-    if (cudaSetDevice(device) != cudaSuccess) return LYON_ERR_CUDA;
+    DeviceGuard device_guard(device);
+    int now = -1;
+    if (cudaGetDevice(&now) != cudaSuccess || now != device) return LYON_ERR_CUDA;
     lyon_cuda_ctx* c = new lyon_cuda_ctx();
     c->device = device;
     if (const char* e = getenv("LYON_PIPE")) c->wt_mode = strcmp(e, "wtile") == 0 ? 1 : 0;  // experiments: warp tiles
@@ -1696,7 +1726,11 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
 
 void lyon_cuda_destroy(lyon_cuda_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard device_guard(c->device);
+    host_pipe_destroy(c->host_pipe);
+    c->host_pipe = nullptr;
+    comm_state_destroy(c->comm);
+    c->comm = nullptr;
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_pt, &c->seg_off, &c->seg_tsplit, &c->seg_id, &c->pos, &c->t,   &c->segfs,
                       &c->len,    &c->adv,     &c->voff,       &c->toff,   &c->jcode, &c->full_list, &c->sp_end_slot, &c->desc, &c->misc,
@@ -1711,12 +1745,14 @@ void lyon_cuda_destroy(lyon_cuda_ctx* c) {
 }
 
 int lyon_cuda_set_stream(lyon_cuda_ctx* c, void* stream) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->stream = (cudaStream_t)stream;
     return LYON_OK;
 }
 int lyon_cuda_synchronize(lyon_cuda_ctx* c) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return LYON_OK;
@@ -1727,32 +1763,46 @@ uint64_t lyon_cuda_workspace_bytes(const lyon_cuda_ctx* c) { return c ? c->ws_by
 
 int lyon_cuda_flatten_cubics_count(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
                                    uint64_t* total) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_count<4>(c, d_ctrl, n, tol, d_offsets, total);
 }
 int lyon_cuda_flatten_cubics_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, const uint64_t* d_offsets,
                                   uint64_t total, float* d_points, float* d_t) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_emit<4>(c, d_ctrl, n, tol, d_offsets, total, d_points, d_t);
 }
 int lyon_cuda_flatten_quadratics_count(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
                                        uint64_t* total) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_count<3>(c, d_ctrl, n, tol, d_offsets, total);
 }
 int lyon_cuda_flatten_quadratics_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol,
                                       const uint64_t* d_offsets, uint64_t total, float* d_points, float* d_t) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_emit<3>(c, d_ctrl, n, tol, d_offsets, total, d_points, d_t);
 }
 
 int lyon_cuda_flatten_cubics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
                                    float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_fused<4>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
 }
 int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets,
                                        float* d_points, uint64_t point_capacity, float* d_t, uint64_t* total_points) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     return flatten_fused<3>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
 }
 
 int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, uint64_t* n_out_verbs,
                                   uint64_t* n_out_points) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     if (!c || !b || !n_out_verbs || !n_out_points) return LYON_ERR_INVALID_ARGUMENT;
     *n_out_verbs = *n_out_points = 0;
     c->pf_planned = false;
@@ -1811,6 +1861,8 @@ int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, fl
 }
 int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* c, uint8_t* d_out_verbs, float* d_out_points, uint32_t* d_out_path_verb_begin,
                                  uint32_t* d_out_path_point_begin) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_PATH_FLATTEN);
     if (!c || !d_out_path_verb_begin || !d_out_path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
     if (!c->pf_planned) {
         c->err = "lyon_cuda_flatten_paths_emit without a successful lyon_cuda_flatten_paths_count";
@@ -1836,6 +1888,8 @@ int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* c, uint8_t* d_out_verbs, float* 
 
 int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, uint64_t* n_vertices,
                           uint64_t* n_indices) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     if (!c || !b || !o || !n_vertices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
     *n_vertices = *n_indices = 0;
     c->planned = false;
@@ -1961,6 +2015,8 @@ int lyon_cuda_stroke_plan(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon
 
 int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint32_t* d_indices, uint64_t vertex_base,
                           uint64_t* d_path_vertex_end, uint64_t* d_path_index_end) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_STROKE);
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     if (!c->planned) {
         c->err = "lyon_cuda_stroke_emit without a successful lyon_cuda_stroke_plan";
@@ -2010,6 +2066,7 @@ int lyon_cuda_stroke_emit(lyon_cuda_ctx* c, lyon_stroke_vertex* d_vertices, uint
 
 // Reads back the device-side consistency flag of the last emit (plan/emit divergence => LYON_ERR_INTERNAL).
 int lyon_cuda_check(lyon_cuda_ctx* c) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     if (c->tile_misc.p) {
         TRY(fetch_tile_totals(c));
@@ -2025,6 +2082,7 @@ int lyon_cuda_check(lyon_cuda_ctx* c) {
 }
 
 int lyon_cuda_enable_timing(lyon_cuda_ctx* c, int on) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c) return LYON_ERR_INVALID_ARGUMENT;
     if (on && !c->ev0) {
         CU_TRY(c, cudaEventCreate(&c->ev0));
@@ -2035,6 +2093,7 @@ int lyon_cuda_enable_timing(lyon_cuda_ctx* c, int on) {
     return LYON_OK;
 }
 int lyon_cuda_last_kernel_ms(lyon_cuda_ctx* c, float* ms) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c || !ms) return LYON_ERR_INVALID_ARGUMENT;
     *ms = 0.0f;
     if (!c->ev_valid) return LYON_ERR_INVALID_ARGUMENT;
@@ -2044,6 +2103,7 @@ int lyon_cuda_last_kernel_ms(lyon_cuda_ctx* c, float* ms) {
 }
 
 int lyon_cuda_rebase_indices(lyon_cuda_ctx* c, uint32_t* d_indices, uint64_t n_indices, uint64_t n_vertices, uint64_t vertex_base) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c || (n_indices && !d_indices)) return LYON_ERR_INVALID_ARGUMENT;
     // ids handed out become vertex_base .. vertex_base + V - 1 and must stay <= u32::MAX - 1 (geometry_builder.rs:342-346)
     if (n_vertices && vertex_base + n_vertices - 1ull > 0xFFFFFFFEull) return LYON_ERR_TOO_MANY_VERTICES;
@@ -2059,6 +2119,8 @@ int lyon_cuda_rebase_indices(lyon_cuda_ctx* c, uint32_t* d_indices, uint64_t n_i
 
 int lyon_cuda_interpolate_attributes(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_vertex* d_vertices,
                                      uint64_t n_vertices, const uint64_t* d_path_vertex_end, float* d_out) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     if (!c || !b) return LYON_ERR_INVALID_ARGUMENT;
     if (b->num_attributes == 0 || n_vertices == 0) return LYON_OK;  // nothing to interpolate
     if (!d_vertices || !d_path_vertex_end || !d_out || !b->verbs || !b->points || !b->path_verb_begin || !b->path_point_begin ||
@@ -2095,6 +2157,8 @@ int lyon_cuda_set_pipeline(lyon_cuda_ctx* c, int pipeline) {
 int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyon_stroke_options* o, lyon_stroke_vertex* d_vertices,
                            uint64_t vertex_capacity, uint32_t* d_indices, uint64_t index_capacity, uint64_t vertex_base,
                            uint64_t* d_path_vertex_end, uint64_t* d_path_index_end, uint64_t* n_vertices, uint64_t* n_indices) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
     if (!c || !b || !o || !n_vertices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
     *n_vertices = *n_indices = 0;
     c->planned = false;
@@ -2156,6 +2220,7 @@ int lyon_cuda_stroke_fused(lyon_cuda_ctx* c, const lyon_path_batch* b, const lyo
 int lyon_cuda_tessellate_paths(lyon_cuda_ctx* c, const lyon_path_batch* hb, const lyon_stroke_options* o,
                                lyon_stroke_vertex** h_vertices, uint64_t* n_vertices, uint32_t** h_indices,
                                uint64_t* n_indices) {
+    DeviceGuard device_guard(c ? c->device : -1);
     if (!c || !hb || !o || !h_vertices || !n_vertices || !h_indices || !n_indices) return LYON_ERR_INVALID_ARGUMENT;
     *h_vertices = nullptr;
     *h_indices = nullptr;
@@ -2228,6 +2293,9 @@ int lyon_cuda_tessellate_paths(lyon_cuda_ctx* c, const lyon_path_batch* hb, cons
 void lyon_cuda_free_host(void* p) { free(p); }
 
 }  // extern "C"
+
+#include "host_pipeline.cuh"
+#include "sharded.cuh"
 
 #ifdef LYON_PHASE_TIMING
 // Debug builds only (tools/phase_profile.py): read and reset the per-phase cycle counters of k_stroke_tile.

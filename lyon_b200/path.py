@@ -491,7 +491,7 @@ def _sinf(a):
 
 
 def _fast_atan2(y, x):
-    """euclid `Trig::fast_atan2` for f32 (euclid 0.22.9 src/trig.rs; the oracle's formula, oracle/lyon_oracle.hpp)."""
+    """euclid `Trig::fast_atan2` for f32 (euclid 0.22.9 src/trig.rs; the same polynomial as lyon_b200/csrc/device_math.cuh)."""
     f = _f32
     pi = f(math.pi)
     xa, ya = f(abs(x)), f(abs(y))

@@ -166,6 +166,60 @@ class DeviceTessellator:
         out = (vertices[:nv.value], indices[:ni.value])
         return out + (pve, pie) if with_ranges else out
 
+    # ---- multi-GPU (lyon_cuda_comm_* / lyon_cuda_stroke_fused_sharded) ---------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """The 128-byte NCCL id rank 0 creates; the application hands it to every rank (any transport)."""
+        buf = (ctypes.c_uint8 * 128)()
+        st = self.L.lyon_cuda_comm_unique_id(buf)
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """Collective: join the communicator of the job (one context per GPU)."""
+        assert len(unique_id) == 128
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        with self.torch.cuda.device(self.device):
+            st = self.L.lyon_cuda_comm_init(self.ctx, buf, int(rank), int(nranks))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        self.comm_rank, self.comm_size = int(rank), int(nranks)
+
+    def comm_destroy(self):
+        self.L.lyon_cuda_comm_destroy(self.ctx)
+
+    def stroke_fused_sharded(self, dbatch: DeviceBatch, options: StrokeOptions, vertices=None, indices=None):
+        """Collective single-pass stroke of this rank's slice: fused kernels with slice-local ids, the all-gather of
+        {V_r, I_r} and the index rebase, all enqueued on the context's stream.  Returns (vertices[:nv], indices[:ni],
+        vertex_base, totals[nranks, 2])."""
+        torch = self.torch
+        own = vertices is None or indices is None
+        if own:
+            vertices, indices = getattr(self, "_own_v", None), getattr(self, "_own_i", None)
+            if vertices is None:
+                vertices = self._own_v = torch.empty((0, 8), dtype=torch.float32, device=self.device)
+                indices = self._own_i = torch.empty((0,), dtype=torch.int32, device=self.device)
+        nv, ni, base = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        totals = np.zeros((self.comm_size, 2), dtype=np.uint64)
+        cb, co = dbatch.c_struct(), options.to_c()
+        for attempt in range(2):
+            st = self.L.lyon_cuda_stroke_fused_sharded(
+                self.ctx, ctypes.byref(cb), ctypes.byref(co), vertices.data_ptr(), vertices.shape[0], indices.data_ptr(),
+                indices.shape[0], None, None, ctypes.byref(nv), ctypes.byref(ni), ctypes.byref(base),
+                totals.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+            if st == _ffi.ERR_BUFFER_TOO_SMALL and attempt == 0:
+                # some rank's buffers were too small: every rank calls again (the exchange is collective)
+                if own and (nv.value > vertices.shape[0] or ni.value > indices.shape[0]):
+                    del vertices, indices
+                    self._own_v = self._own_i = None
+                    vertices = self._own_v = torch.empty((nv.value + nv.value // 64 + 64, 8), dtype=torch.float32, device=self.device)
+                    indices = self._own_i = torch.empty((ni.value + ni.value // 64 + 256,), dtype=torch.int32, device=self.device)
+                continue
+            break
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return vertices[:nv.value], indices[:ni.value], int(base.value), totals
+
     def rebase_indices(self, indices, n_vertices: int, vertex_base: int):
         """indices += vertex_base in place (lyon_cuda_rebase_indices): global index rebasing after a single-pass emit."""
         st = self.L.lyon_cuda_rebase_indices(self.ctx, indices.data_ptr(), int(indices.shape[0]), int(n_vertices), int(vertex_base))
@@ -380,15 +434,38 @@ def flatten_quadratics(ctrl: np.ndarray, tolerance: float, tessellator: Optional
     return tuple(x.cpu().numpy().view(np.uint64) if k == 0 else x.cpu().numpy() for k, x in enumerate(out))
 
 
+class _PinnedArray:
+    """A numpy view of page-locked host memory from lyon_cuda_host_alloc (freed with the object)."""
+
+    def __init__(self, L, nbytes: int):
+        self.L = L
+        self.ptr = ctypes.c_void_p()
+        st = L.lyon_cuda_host_alloc(ctypes.byref(self.ptr), max(int(nbytes), 1))
+        if st != _ffi.LYON_OK:
+            raise MemoryError(f"lyon_cuda_host_alloc({nbytes}) failed ({st})")
+        self.nbytes = max(int(nbytes), 1)
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * self.nbytes).from_address(self.ptr.value))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.L.lyon_cuda_host_free(self.ptr)
+                self.ptr = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
 class HostPipeline:
     """End-to-end host->host tessellation of a large batch: the public call a lyon user makes
-    (`tessellate_paths(&[Path], &StrokeOptions) -> VertexBuffers`) for batches whose output does not have to fit
-    (or wait) in one piece.  The batch is cut into chunks of paths; two contexts on two streams alternate so that
-    the PCIe download of chunk i overlaps the upload + kernels of chunk i+1.  Chunk c is emitted with
+    (`tessellate_paths(&[Path], &StrokeOptions) -> VertexBuffers`), a thin wrapper over the C entry point
+    `lyon_cuda_tessellate_paths_into` (include/lyon_cuda.h), which cuts the batch into chunks of paths and alternates two
+    streams so that the PCIe download of chunk i overlaps the upload + kernels of chunk i + 1.  Chunk c is emitted with
     vertex_base = vertices of chunks < c, so the concatenated host buffers equal the one-shot result.
 
     Inputs are staged in pinned host memory once (`stage`), outputs land in pinned host arrays that are reused
     across calls (like bench/tess reuses its VertexBuffers)."""
+
+    API = "lyon_cuda_tessellate_paths_into"
 
     def __init__(self, device=None, chunk_paths: int = 32768):
         import torch
@@ -396,83 +473,53 @@ class HostPipeline:
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.chunk_paths = int(chunk_paths)
-        with torch.cuda.device(self.device):
-            self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
-            self.tz = [DeviceTessellator(self.device.index, stream=s) for s in self.streams]
-        self.out_v = None
-        self.out_i = None
+        self.tz = DeviceTessellator(self.device.index)
+        self.L = self.tz.L
+        self.out_v = self.out_i = None
+        self.cap_v = self.cap_i = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def stage(self, batch: PathBatch):
-        """Pin the input batch (outside any timed region) and precompute chunk boundaries."""
-        torch = self.torch
+        """Copy the input batch into pinned host memory (outside any timed region)."""
         self.batch = batch
-        self.p_verbs = torch.from_numpy(np.ascontiguousarray(batch.verbs, np.uint8)).pin_memory()
-        self.p_points = torch.from_numpy(np.ascontiguousarray(batch.points, np.float32).reshape(-1)).pin_memory()
-        self.vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32).astype(np.int64)
-        self.pb = np.ascontiguousarray(batch.path_point_begin, np.uint32).astype(np.int64)
-        n = batch.n_paths
-        self.cuts = list(range(0, n, self.chunk_paths)) + [n]
-        self.p_ranges, self.p_pranges = [], []
-        for lo, hi in zip(self.cuts[:-1], self.cuts[1:]):
-            self.p_ranges.append(torch.from_numpy((self.vb[lo:hi + 1] - self.vb[lo]).astype(np.int32)).pin_memory())
-            self.p_pranges.append(torch.from_numpy((self.pb[lo:hi + 1] - self.pb[lo]).astype(np.int32)).pin_memory())
+        nv, npt, np_ = int(batch.verbs.shape[0]), int(batch.points.shape[0]), batch.n_paths
+        self._in = [_PinnedArray(self.L, nv), _PinnedArray(self.L, 8 * npt), _PinnedArray(self.L, 4 * (np_ + 1)),
+                    _PinnedArray(self.L, 4 * (np_ + 1))]
+        self._in[0].array[:nv] = np.ascontiguousarray(batch.verbs, np.uint8)
+        self._in[1].array[:8 * npt] = np.ascontiguousarray(batch.points, np.float32).reshape(-1).view(np.uint8)
+        self._in[2].array[:4 * (np_ + 1)] = np.ascontiguousarray(batch.path_verb_begin, np.uint32).view(np.uint8)
+        self._in[3].array[:4 * (np_ + 1)] = np.ascontiguousarray(batch.path_point_begin, np.uint32).view(np.uint8)
+        self.cbatch = _ffi.CPathBatch(self._in[0].ptr, self._in[1].ptr, self._in[2].ptr, self._in[3].ptr, np_,
+                                      batch.num_attributes, nv, npt)
+        self.h2d_bytes = nv + 8 * npt + 8 * (np_ + 1)
+
+    def _alloc_outputs(self, cap_v: int, cap_i: int):
+        self.out_v = self.out_i = None  # release the old pinned buffers first
+        self.out_v = _PinnedArray(self.L, 32 * cap_v)
+        self.out_i = _PinnedArray(self.L, 4 * cap_i)
+        self.cap_v, self.cap_i = cap_v, cap_i
 
     def run(self, options: StrokeOptions):
-        """One end-to-end pass. Returns (n_vertices, n_indices); results are in self.out_v[:nv], self.out_i[:ni]."""
-        torch = self.torch
-        batch = self.batch
-        tot_v = tot_i = 0
-        self.h2d_bytes = self.d2h_bytes = 0
-        with torch.cuda.device(self.device):
-            for c, (lo, hi) in enumerate(zip(self.cuts[:-1], self.cuts[1:])):
-                k = c & 1
-                s, tz = self.streams[k], self.tz[k]
-                v0, v1, p0, p1 = int(self.vb[lo]), int(self.vb[hi]), int(self.pb[lo]), int(self.pb[hi])
-                with torch.cuda.stream(s):
-                    d = DeviceBatch.__new__(DeviceBatch)
-                    d.n_paths, d.num_attributes, d.n_verbs, d.n_points = hi - lo, batch.num_attributes, v1 - v0, p1 - p0
-                    d.verbs = self.p_verbs[v0:v1].to(self.device, non_blocking=True)
-                    d.points = self.p_points[2 * p0:2 * p1].to(self.device, non_blocking=True)
-                    d.path_verb_begin = self.p_ranges[c].to(self.device, non_blocking=True)
-                    d.path_point_begin = self.p_pranges[c].to(self.device, non_blocking=True)
-                    self.h2d_bytes += (v1 - v0) + 8 * (p1 - p0) + 8 * (hi - lo + 1)
-                    # single pass into this context's own grow-only device buffers (syncs stream k only)
-                    dv, di = tz.stroke_fused(d, options, vertex_base=tot_v)
-                    nv, ni = int(dv.shape[0]), int(di.shape[0])
-                    if tot_v + nv > 0xFFFFFFFF:
-                        raise TooManyVertices(_ffi.ERR_TOO_MANY_VERTICES, "TooManyVertices")
-                    if self.out_v is None or self.out_v.shape[0] < tot_v + nv or self.out_i.shape[0] < tot_i + ni:
-                        self._grow_outputs(tot_v + nv, tot_i + ni, c + 1, tot_v, tot_i)
-                    self.out_v[tot_v:tot_v + nv].copy_(dv[:nv], non_blocking=True)
-                    self.out_i[tot_i:tot_i + ni].copy_(di[:ni], non_blocking=True)
-                    self.d2h_bytes += 32 * nv + 4 * ni
-                tot_v += nv
-                tot_i += ni
-            for s in self.streams:
-                s.synchronize()
-            for tz in self.tz:
-                tz.check()
-        return tot_v, tot_i
-
-    def _grow_outputs(self, need_v, need_i, chunks_done, have_v, have_i):
-        """Pinned output arrays sized by extrapolating from the chunks seen so far (first call only, in practice)."""
-        torch = self.torch
-        n_chunks = len(self.cuts) - 1
-        scale = n_chunks / max(chunks_done, 1) * 1.05
-        new_v = torch.empty((int(need_v * scale) + 1024, 8), dtype=torch.float32).pin_memory()
-        new_i = torch.empty((int(need_i * scale) + 4096,), dtype=torch.int32).pin_memory()
-        for s in self.streams:
-            s.synchronize()
-        if self.out_v is not None and have_v:
-            new_v[:have_v].copy_(self.out_v[:have_v])
-            new_i[:have_i].copy_(self.out_i[:have_i])
-        self.out_v, self.out_i = new_v, new_i
+        """One end-to-end pass. Returns (n_vertices, n_indices); results are in the pinned arrays (`result`)."""
+        copts = options.to_c()
+        nv, ni = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        for _attempt in range(2):
+            st = self.L.lyon_cuda_tessellate_paths_into(
+                self.tz.ctx, ctypes.byref(self.cbatch), ctypes.byref(copts),
+                self.out_v.ptr if self.out_v else None, self.cap_v, self.out_i.ptr if self.out_i else None, self.cap_i,
+                self.chunk_paths, ctypes.byref(nv), ctypes.byref(ni))
+            if st != _ffi.ERR_BUFFER_TOO_SMALL:
+                break
+            self._alloc_outputs(int(nv.value) + 1024, int(ni.value) + 4096)  # exact sizes are known now (first call only)
+        if st != _ffi.LYON_OK:
+            _raise(self.L, self.tz.ctx, st)
+        self.d2h_bytes = 32 * int(nv.value) + 4 * int(ni.value)
+        return int(nv.value), int(ni.value)
 
     def result(self, nv: int, ni: int) -> VertexBuffers:
-        return VertexBuffers(self.out_v[:nv].numpy().view(STROKE_VERTEX_DTYPE).reshape(-1),
-                             self.out_i[:ni].numpy().view(np.uint32))
+        return VertexBuffers(self.out_v.array[:32 * nv].view(STROKE_VERTEX_DTYPE).reshape(-1),
+                             self.out_i.array[:4 * ni].view(np.uint32))
 
     def launch_count(self) -> int:
-        return sum(t.launch_count() for t in self.tz)
+        return self.tz.launch_count()

@@ -31,7 +31,9 @@ pub struct lyon_stroke_options {
 }
 
 /// `StrokeVertexGpu`: everything `StrokeVertex` exposes (crates/tessellation/src/stroke.rs:2656-2747).
-#[repr(C, align(16))]
+/// 32 bytes, natural alignment 4 like the C typedef; DEVICE vertex arrays handed to the library must be 32-byte aligned
+/// (the kernels write a vertex with one 256-bit store; the entry points check and return LYON_ERR_INVALID_ARGUMENT).
+#[repr(C)]
 #[derive(Copy, Clone, Debug, Default, PartialEq)]
 pub struct lyon_stroke_vertex {
     pub position_on_path: [f32; 2],
@@ -105,4 +107,18 @@ extern "C" {
                                       options: *const lyon_stroke_options, h_vertices: *mut *mut lyon_stroke_vertex,
                                       n_vertices: *mut u64, h_indices: *mut *mut u32, n_indices: *mut u64) -> c_int;
     pub fn lyon_cuda_free_host(p: *mut c_void);
+    pub fn lyon_cuda_tessellate_paths_into(ctx: *mut lyon_cuda_ctx, h_batch: *const lyon_path_batch,
+                                           options: *const lyon_stroke_options, h_vertices: *mut lyon_stroke_vertex,
+                                           vertex_capacity: u64, h_indices: *mut u32, index_capacity: u64,
+                                           chunk_paths: u32, n_vertices: *mut u64, n_indices: *mut u64) -> c_int;
+    pub fn lyon_cuda_host_alloc(p: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn lyon_cuda_host_free(p: *mut c_void);
+    pub fn lyon_cuda_comm_unique_id(id128: *mut u8) -> c_int;
+    pub fn lyon_cuda_comm_init(ctx: *mut lyon_cuda_ctx, id128: *const u8, rank: c_int, nranks: c_int) -> c_int;
+    pub fn lyon_cuda_comm_destroy(ctx: *mut lyon_cuda_ctx) -> c_int;
+    pub fn lyon_cuda_stroke_fused_sharded(ctx: *mut lyon_cuda_ctx, d_batch: *const lyon_path_batch,
+                                          options: *const lyon_stroke_options, d_vertices: *mut lyon_stroke_vertex,
+                                          vertex_capacity: u64, d_indices: *mut u32, index_capacity: u64,
+                                          d_path_vertex_end: *mut u64, d_path_index_end: *mut u64, n_vertices: *mut u64,
+                                          n_indices: *mut u64, vertex_base: *mut u64, h_totals: *mut u64) -> c_int;
 }

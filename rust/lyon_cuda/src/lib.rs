@@ -161,20 +161,32 @@ impl CudaTessellator {
             n_points: batch.points.len() as u32,
         };
         let co = options_to_c(options);
-        let (mut pv, mut pi) = (ptr::null_mut(), ptr::null_mut());
+        // `lyon_cuda_tessellate_paths_into`: chunked, double-buffered upload / kernels / download into buffers the caller
+        // owns.  The first call with empty buffers returns the exact sizes (LYON_ERR_BUFFER_TOO_SMALL), the second fills
+        // them; a caller that keeps its VertexBuffers across frames (bench/tess/src/main.rs:186-196) pays for one call.
+        let mut out: VertexBuffers<StrokeVertexGpu, u32> = VertexBuffers::new();
         let (mut nv, mut ni) = (0u64, 0u64);
-        let st = unsafe { ffi::lyon_cuda_tessellate_paths(self.ctx, &hb, &co, &mut pv, &mut nv, &mut pi, &mut ni) };
-        if st != ffi::LYON_OK {
-            return Err(status_to_error(st));
+        for _ in 0..2 {
+            let st = unsafe {
+                ffi::lyon_cuda_tessellate_paths_into(self.ctx, &hb, &co, out.vertices.as_mut_ptr(), out.vertices.capacity() as u64,
+                                                     out.indices.as_mut_ptr(), out.indices.capacity() as u64, 0, &mut nv, &mut ni)
+            };
+            if st == ffi::LYON_ERR_BUFFER_TOO_SMALL {
+                out.vertices.reserve_exact(nv as usize);
+                out.indices.reserve_exact(ni as usize);
+                continue;
+            }
+            if st != ffi::LYON_OK {
+                return Err(status_to_error(st));
+            }
+            // the library wrote nv vertices / ni indices into the reserved capacity (nothing when they are 0)
+            unsafe {
+                out.vertices.set_len(nv as usize);
+                out.indices.set_len(ni as usize);
+            }
+            return Ok(out);
         }
-        let mut out = VertexBuffers::with_capacity(nv as usize, ni as usize);
-        unsafe {
-            out.vertices.extend_from_slice(std::slice::from_raw_parts(pv, nv as usize));
-            out.indices.extend_from_slice(std::slice::from_raw_parts(pi, ni as usize));
-            ffi::lyon_cuda_free_host(pv as *mut _);
-            ffi::lyon_cuda_free_host(pi as *mut _);
-        }
-        Ok(out)
+        Err(status_to_error(ffi::LYON_ERR_BUFFER_TOO_SMALL))
     }
 }
 

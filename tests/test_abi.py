@@ -61,3 +61,31 @@ def test_wide_vertex_stores_survive_ptxas():
     lib = g.build_cuda()
     r = subprocess.run([sys.executable, str(root / "tools" / "check_sass.py"), str(lib)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _c_prototypes(header: str):
+    """{name: number of parameters} of every function include/lyon_cuda.h declares."""
+    text = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(lyon_cuda_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_rust_ffi_declares_the_header():
+    """rust/lyon_cuda cannot be compiled in this image (no cargo / rustc), so its extern block is checked mechanically
+    against the header: the same functions, each with the same number of parameters."""
+    header = (O.ROOT / "include" / "lyon_cuda.h").read_text()
+    rust = (O.ROOT / "rust" / "lyon_cuda" / "src" / "ffi.rs").read_text()
+    c = _c_prototypes(header)
+    assert len(c) >= 30
+    r = {}
+    for m in re.finditer(r"pub fn (lyon_cuda_\w+)\s*\(([^;]*?)\)\s*(?:->\s*[^;]+)?;", rust, flags=re.S):
+        params = m.group(2).strip()
+        r[m.group(1)] = 0 if not params else len([p for p in params.split(",") if p.strip()])
+    assert set(r) == set(c), f"missing in ffi.rs: {sorted(set(c) - set(r))}; unknown: {sorted(set(r) - set(c))}"
+    for name, n in c.items():
+        assert r[name] == n, f"{name}: {n} parameters in lyon_cuda.h, {r[name]} in ffi.rs"
+    # the structs the two sides share
+    assert "pub struct lyon_stroke_vertex" in rust and "pub struct lyon_path_batch" in rust and "pub struct lyon_stroke_options" in rust
