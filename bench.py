@@ -303,6 +303,8 @@ def main():
         tz._own_v = tz._own_i = None
         torch.cuda.empty_cache()
         # >= 16 chunks per rank, so that the two alternating streams reach their steady state at every N
+        from lyon_b200.numa import bind_to_device_node
+        numa_node = bind_to_device_node(local_rank)  # pinned buffers on the GPU's own memory node (best effort)
         pipe = HostPipeline(local_rank, chunk_paths=max(4096, min(25000, (batch.n_paths + 15) // 16)))
         pipe.stage(batch)
         pipe.run(opts)  # warm-up: sizes + pins the output arrays
@@ -317,7 +319,8 @@ def main():
         e2e = {"value": sum_over_ranks(ev) / e2e_s, "unit": "vertices/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_s * 1e3, "api": "lyon_cuda_tessellate_paths_into (C ABI; "
                "pinned host inputs -> chunked H2D -> fused stroke kernels -> D2H of every vertex and index, two streams)",
-               "chunk_paths": pipe.chunk_paths}
+               "chunk_paths": pipe.chunk_paths, "numa_node": numa_node,
+               "d2h_gbs_per_gpu": pipe.d2h_bytes / e2e_s / 1e9}
         del pipe
         torch.cuda.empty_cache()
 

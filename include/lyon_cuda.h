@@ -120,12 +120,24 @@ int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* ctx, const float* d_ctrl, 
 /* Path-level flattening: the `Flattened` adapter, `path.iter().flattened(tolerance)` (crates/path/src/iterator.rs:125-226,
  * PathEvent::Quadratic / Cubic -> the Line events of `segment.flattened(tolerance)`), for every path of a batch.  The
  * output is a batch in the same encoding (verbs Begin / LineTo / Close / End only; Close stores the first point again)
- * and can be fed back to any entry point.  Paths without custom attributes.  Pass 1 returns the sizes; pass 2 writes
+ * and can be fed back to any entry point.  Custom attributes are interpolated along the curves like the `Flattened`
+ * builder adapter does (crates/path/src/private.rs:56-122: prev[i] * (1 - t) + attr[i] * t, the curve's own attributes
+ * where t == 1.0) and stored after every output endpoint.  Pass 1 returns the sizes; pass 2 writes
  * d_out_verbs[n_out_verbs], d_out_points[2 * n_out_points] and the two n_paths + 1 range arrays. */
 int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, float tolerance, uint64_t* n_out_verbs,
                                   uint64_t* n_out_points);
 int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* ctx, uint8_t* d_out_verbs, float* d_out_points, uint32_t* d_out_path_verb_begin,
                                  uint32_t* d_out_path_point_begin);
+
+/* PathMeasurements::from_path (crates/algorithms/src/measure.rs:140-260) for every path of a batch -- a consumer of
+ * flattening: one Edge {distance, index, t} per Begin (distance unchanged, t 1), per LineTo (distance += |from - to|), per
+ * flattened segment of a curve (for_each_flattened_with_t at max(tolerance, 1e-4): distance += |segment|, t = t.end) and per
+ * Close (distance += |last - first|); `index` is the event's position in its path, the distance runs over the whole path
+ * in f32, event order.  Pass 1 returns the number of edges; pass 2 writes d_distance / d_event_index / d_t (n_edges
+ * each), d_path_edge_begin (n_paths + 1, u64) and d_path_length (n_paths: PathMeasurements::length, measure.rs:262-268). */
+int lyon_cuda_measure_paths_count(lyon_cuda_ctx* ctx, const lyon_path_batch* d_batch, float tolerance, uint64_t* n_edges);
+int lyon_cuda_measure_paths_emit(lyon_cuda_ctx* ctx, float* d_distance, uint32_t* d_event_index, float* d_t,
+                                 uint64_t* d_path_edge_begin, float* d_path_length);
 
 /* ---- stroke tessellation (lyon_tessellation::StrokeTessellator) ------------------------------------ */
 /* Equivalent of, for every path p of the batch in order,

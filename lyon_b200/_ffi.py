@@ -30,6 +30,7 @@ SYMBOLS = [
     "lyon_cuda_flatten_quadratics_count", "lyon_cuda_flatten_quadratics_emit",
     "lyon_cuda_flatten_cubics_fused", "lyon_cuda_flatten_quadratics_fused",
     "lyon_cuda_flatten_paths_count", "lyon_cuda_flatten_paths_emit",
+    "lyon_cuda_measure_paths_count", "lyon_cuda_measure_paths_emit",
     "lyon_cuda_stroke_plan", "lyon_cuda_stroke_emit", "lyon_cuda_check", "lyon_cuda_stroke_fused", "lyon_cuda_rebase_indices", "lyon_cuda_set_pipeline",
     "lyon_cuda_interpolate_attributes",
     "lyon_cuda_enable_timing", "lyon_cuda_last_kernel_ms",
@@ -87,6 +88,8 @@ def lib():
         getattr(L, name).argtypes = [vp, vp, u64, f32, vp, vp, u64, vp, pu64]
     L.lyon_cuda_flatten_paths_count.argtypes = [vp, ctypes.POINTER(CPathBatch), f32, pu64, pu64]
     L.lyon_cuda_flatten_paths_emit.argtypes = [vp, vp, vp, vp, vp]
+    L.lyon_cuda_measure_paths_count.argtypes = [vp, ctypes.POINTER(CPathBatch), f32, pu64]
+    L.lyon_cuda_measure_paths_emit.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lyon_cuda_stroke_plan.argtypes = [vp, ctypes.POINTER(CPathBatch), ctypes.POINTER(CStrokeOptions), pu64, pu64]
     L.lyon_cuda_stroke_emit.argtypes = [vp, vp, vp, u64, vp, vp]
     L.lyon_cuda_check.argtypes = [vp]

@@ -723,8 +723,10 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
 // ---------------------------------------------------------------------------------------------------------
 // Path-level flattening: the `Flattened` adapter (crates/path/src/iterator.rs:125-226) over a whole batch.  Every
 // QuadraticTo / CubicTo becomes the LineTo sequence of its flattened points (for_each_flattened: plain Wang counts, no
-// sharp-turn split -- that one belongs to the stroker); Begin / LineTo / Close / End pass through.  Paths without
-// custom attributes.  One warp per path in both passes; a lane owns a verb and writes its points in order.
+// sharp-turn split -- that one belongs to the stroker); Begin / LineTo / Close / End pass through.  Custom attributes
+// (two per point slot after every endpoint, path.rs:650-665) are interpolated along the curves as the `Flattened` builder
+// adapter does (crates/path/src/private.rs:56-122): prev[i] * (1 - t) + attr[i] * t, the curve's own where t == 1.0.
+// One warp per path in both passes; a lane owns a verb and writes its points in order.
 // ---------------------------------------------------------------------------------------------------------
 struct PfRec {  // per input verb, written by the count pass
     float n;          // Wang count of a curve (f32, possibly non-integer), 1 otherwise
@@ -732,17 +734,18 @@ struct PfRec {  // per input verb, written by the count pass
     uint32_t poff;    // first output point, relative to the path's first output point
     uint32_t pt;      // first stored input point of the verb
 };
-__device__ __forceinline__ uint32_t pf_count(uint8_t verb, const V2* points, uint32_t pt, float tol, float* n_out) {
+__device__ __forceinline__ uint32_t pf_count(uint8_t verb, const V2* points, uint32_t pt, uint32_t a, float tol, float* n_out) {
     float n = 1.0f;
-    if (verb == VERB_CUBIC) n = cubic_wang(seg_from_point(points, pt, 0u), points[pt], points[pt + 1], points[pt + 2], tol);
-    else if (verb == VERB_QUAD) n = quad_wang(seg_from_point(points, pt, 0u), points[pt], points[pt + 1], tol);
+    if (verb == VERB_CUBIC) n = cubic_wang(seg_from_point(points, pt, a), points[pt], points[pt + 1], points[pt + 2], tol);
+    else if (verb == VERB_QUAD) n = quad_wang(seg_from_point(points, pt, a), points[pt], points[pt + 1], tol);
     *n_out = n;
     return (verb == VERB_CUBIC || verb == VERB_QUAD) ? to_u32_or_1(n) : 1u;
 }
 __global__ void __launch_bounds__(256) k_pf_count(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
                                                   const uint32_t* __restrict__ path_verb_begin,
-                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths, float tol,
-                                                  PfRec* __restrict__ rec, uint32_t* __restrict__ path_nv,
+                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths,
+                                                  uint32_t attr_stride, uint32_t pstride, float tol, PfRec* __restrict__ rec,
+                                                  uint32_t* __restrict__ path_nv,
                                                   uint32_t* __restrict__ path_np, Totals* totals) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(256) k_pf_count(const uint8_t* __restrict__ ve
             const uint32_t v = v0 + lane;
             const bool valid = v < ve;
             const uint8_t verb = valid ? verbs[v] : (uint8_t)VERB_END;
-            const uint32_t npts = valid ? verb_point_count(verb, 0u) : 0u;
+            const uint32_t npts = valid ? verb_point_count(verb, attr_stride) : 0u;
             uint32_t inc = npts;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -764,8 +767,9 @@ __global__ void __launch_bounds__(256) k_pf_count(const uint8_t* __restrict__ ve
             }
             const uint32_t pt = pt_run + inc - npts;
             float n = 1.0f;
-            const uint32_t cnt = valid ? pf_count(verb, points, pt, tol, &n) : 0u;
-            const uint32_t pcnt = (valid && verb == VERB_END) ? 0u : cnt;  // End carries no point
+            const uint32_t cnt = valid ? pf_count(verb, points, pt, attr_stride, tol, &n) : 0u;
+            // End carries no point; every other output verb one endpoint and its attribute slots
+            const uint32_t pcnt = (valid && verb == VERB_END) ? 0u : cnt * pstride;  // (pstride 1: PathMeasurements edges)
             unsigned long long iv = cnt, ip = pcnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -794,7 +798,8 @@ __global__ void __launch_bounds__(256) k_pf_count(const uint8_t* __restrict__ ve
 __global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
                                                  const uint32_t* __restrict__ path_verb_begin,
                                                  const uint32_t* __restrict__ path_point_begin, uint32_t n_paths,
-                                                 const PfRec* __restrict__ rec, const unsigned long long* __restrict__ out_v0,
+                                                 uint32_t num_attributes, const PfRec* __restrict__ rec,
+                                                 const unsigned long long* __restrict__ out_v0,
                                                  const unsigned long long* __restrict__ out_p0, uint8_t* __restrict__ out_verbs,
                                                  V2* __restrict__ out_points, uint32_t* __restrict__ out_path_verb_begin,
                                                  uint32_t* __restrict__ out_path_point_begin) {
@@ -812,8 +817,7 @@ __global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ ver
                 out_path_point_begin[n_paths] = (uint32_t)out_p0[n_paths];
             }
         }
-        const V2 first_of_path = points[path_point_begin[path]];
-        (void)first_of_path;
+        const uint32_t A = num_attributes, a = (A + 1u) / 2u;
         for (uint32_t v = vb + lane; v < ve; v += 32u) {
             const uint8_t verb = verbs[v];
             const uint4 q = *reinterpret_cast<const uint4*>(rec + v);
@@ -823,8 +827,12 @@ __global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ ver
             const uint32_t pt = q.w;
             if (verb == VERB_CUBIC || verb == VERB_QUAD) {
                 const bool cubic = verb == VERB_CUBIC;
-                const V2 from = seg_from_point(points, pt, 0u);
-                const V2 to = points[pt + (cubic ? 2u : 1u)];
+                const V2 from = seg_from_point(points, pt, a);
+                const uint32_t nc = cubic ? 2u : 1u;
+                const V2 to = points[pt + nc];
+                // attributes of the curve's two endpoints: the slots after `to`, and the slots right before the control points
+                const float* at = reinterpret_cast<const float*>(points + pt + nc + 1u);
+                const float* ap = reinterpret_cast<const float*>(points + (pt >= a ? pt - a : 0u));
                 V2 a1, a2, a3 = v2(0.0f, 0.0f);
                 if (cubic) {
                     const CubicPoly c = cubic_poly(from, points[pt], points[pt + 1], to);
@@ -850,13 +858,112 @@ __global__ void __launch_bounds__(256) k_pf_emit(const uint8_t* __restrict__ ver
                         }
                     }
                     ov[k] = VERB_LINE;
-                    op[k] = pos;
+                    V2* o = op + (size_t)k * (1u + a);
+                    o[0] = pos;
+                    if (a) {
+                        const float tt = k + 1u < cnt ? t : 1.0f;
+                        float* oa = reinterpret_cast<float*>(o + 1);
+                        for (uint32_t i = 0; i < 2u * a; ++i)
+                            oa[i] = i >= A ? 0.0f : (tt == 1.0f ? at[i] : ap[i] * (1.0f - tt) + at[i] * tt);
+                    }
                 }
             } else {
                 ov[0] = verb;
-                if (verb != VERB_END) op[0] = points[pt];  // Begin / LineTo / Close (the first point stored again)
+                if (verb != VERB_END)  // Begin / LineTo / Close (the first point stored again), with the attribute slots
+                    for (uint32_t i = 0; i <= a; ++i) op[i] = points[pt + i];
             }
         }
+    }
+}
+
+// PathMeasurements::initialize (crates/algorithms/src/measure.rs:170-257) for every path of a batch: one Edge {distance,
+// index, t} per Begin (distance unchanged, t 1), per LineTo (distance += |from - to|), per flattened segment of a curve
+// (for_each_flattened_with_t: distance += |segment|, t = t.end) and per Close (distance += |last - first|); `index` is
+// the event's position in the path.  One warp per path: a lane writes the lengths of its verb's edges, then the warp
+// replays the f32 running sum in event order -- 32 edges per step, every lane following the same chain through
+// shuffles and keeping the value at its own position (the sum is sequential by definition: another order rounds differently).
+__global__ void __launch_bounds__(256) k_pm_emit(const uint8_t* __restrict__ verbs, const V2* __restrict__ points,
+                                                 const uint32_t* __restrict__ path_verb_begin, uint32_t n_paths, uint32_t attr_stride,
+                                                 const PfRec* __restrict__ rec, const unsigned long long* __restrict__ edge0,
+                                                 float* __restrict__ distance, uint32_t* __restrict__ index, float* __restrict__ t_out,
+                                                 unsigned long long* __restrict__ path_edge_begin, float* __restrict__ path_length) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t a = attr_stride;
+    for (uint32_t path = warp; path < n_paths; path += nwarps) {
+        const uint32_t vb = path_verb_begin[path], ve = path_verb_begin[path + 1];
+        const unsigned long long e0 = edge0[path], e1 = edge0[path + 1];
+        if (lane == 0u) {
+            path_edge_begin[path] = e0;
+            if (path + 1u == n_paths) path_edge_begin[n_paths] = e1;
+        }
+        for (uint32_t v = vb + lane; v < ve; v += 32u) {
+            const uint8_t verb = verbs[v];
+            if (verb == VERB_END) continue;  // an open sub-path's End has no edge
+            const uint4 q = *reinterpret_cast<const uint4*>(rec + v);
+            const float n = __uint_as_float(q.x);
+            const unsigned long long e = e0 + q.z;
+            const uint32_t pt = q.w, ev = v - vb;
+            if (verb == VERB_CUBIC || verb == VERB_QUAD) {
+                const bool cubic = verb == VERB_CUBIC;
+                const V2 from = seg_from_point(points, pt, a);
+                const V2 to = points[pt + (cubic ? 2u : 1u)];
+                V2 a1, a2, a3 = v2(0.0f, 0.0f);
+                if (cubic) {
+                    const CubicPoly c = cubic_poly(from, points[pt], points[pt + 1], to);
+                    a1 = c.a1; a2 = c.a2; a3 = c.a3;
+                } else {
+                    const QuadPoly c = quad_poly(from, points[pt], to);
+                    a1 = c.a1; a2 = c.a2;
+                }
+                const uint32_t cnt = to_u32_or_1(n);
+                const float step = 1.0f / n;
+                float t = 0.0f;
+                V2 prev = from;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    V2 pos = to;
+                    float te = 1.0f;
+                    if (k + 1u < cnt) {
+                        t = t + step;
+                        te = t;
+                        float u = t;
+                        pos = from + a1 * u;
+                        u = u * t;
+                        pos = pos + a2 * u;
+                        if (cubic) {
+                            u = u * t;
+                            pos = pos + a3 * u;
+                        }
+                    }
+                    distance[e + k] = length(pos - prev);
+                    index[e + k] = ev;
+                    t_out[e + k] = te;
+                    prev = pos;
+                }
+            } else {
+                // Begin: distance unchanged (+0 is exact); LineTo / Close: |from - to| with `to` the stored point
+                distance[e] = verb == VERB_BEGIN ? 0.0f : length(seg_from_point(points, pt, a) - points[pt]);
+                index[e] = ev;
+                t_out[e] = 1.0f;
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        float acc = 0.0f;
+        for (unsigned long long b = e0; b < e1; b += 32ull) {
+            const bool in = b + lane < e1;
+            const float x = in ? distance[b + lane] : 0.0f;
+            float mine = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                acc = acc + __shfl_sync(0xffffffffu, x, j);  // (+0 beyond the end: exact)
+                if ((int)lane == j) mine = acc;
+            }
+            if (in) distance[b + lane] = mine;
+        }
+        if (lane == 0u) path_length[path] = acc;
+        __syncwarp();
     }
 }
 
@@ -1070,6 +1177,7 @@ struct lyon_cuda_ctx {
     DevBuf attr_kind;  // lyon_cuda_interpolate_attributes: per point, the point count of the curve ending there
     DevBuf pf_rec;  // path-level flattening: per-verb records (counts reuse vw_nv / vw_nt / vw_v0 / vw_t0)
     bool pf_planned = false;
+    bool pf_measure = false;  // ... by lyon_cuda_measure_paths_count (edges) rather than lyon_cuda_flatten_paths_count
     lyon_path_batch pf_batch{};
     lyon_path_batch vw_batch{};
     lyon_path_batch tile_batch{};
@@ -1799,18 +1907,14 @@ int lyon_cuda_flatten_quadratics_fused(lyon_cuda_ctx* c, const float* d_ctrl, ui
     return flatten_fused<3>(c, d_ctrl, n, tol, d_offsets, d_points, point_capacity, d_t, total_points);
 }
 
-int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, uint64_t* n_out_verbs,
-                                  uint64_t* n_out_points) {
-    DeviceGuard device_guard(c ? c->device : -1);
-    if (c) drop_plans(c, KEEP_NONE);
-    if (!c || !b || !n_out_verbs || !n_out_points) return LYON_ERR_INVALID_ARGUMENT;
+// Count pass shared by lyon_cuda_flatten_paths_count and lyon_cuda_measure_paths_count (`measure`: the second number is the
+// number of PathMeasurements edges instead of output points).
+static int pf_count_impl(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, bool measure, uint64_t* n_out_verbs,
+                         uint64_t* n_out_points) {
     *n_out_verbs = *n_out_points = 0;
     c->pf_planned = false;
+    c->pf_measure = measure;
     if (!(tol > 0.0f)) return LYON_ERR_UNSUPPORTED_PARAMETER;  // ToleranceIsNaN / non-positive
-    if (b->num_attributes != 0) {
-        c->err = "lyon_cuda_flatten_paths: paths with custom attributes are not supported";
-        return LYON_ERR_UNSUPPORTED_PARAMETER;
-    }
     c->pf_batch = *b;
     if (b->n_paths == 0 || b->n_verbs == 0) {
         c->pf_planned = true;
@@ -1832,7 +1936,9 @@ int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, fl
     unsigned blocks = (np + 7u) / 8u;
     if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
     k_pf_count<<<blocks, 256, 0, c->stream>>>(b->verbs, reinterpret_cast<const V2*>(b->points), b->path_verb_begin,
-                                             b->path_point_begin, np, tol, (PfRec*)c->pf_rec.p, (uint32_t*)c->vw_nv.p,
+                                             b->path_point_begin, np, (b->num_attributes + 1u) / 2u,
+                                             measure ? 1u : 1u + (b->num_attributes + 1u) / 2u, tol, (PfRec*)c->pf_rec.p,
+                                             (uint32_t*)c->vw_nv.p,
                                              (uint32_t*)c->vw_nt.p, d_totals(c));
     k_scan_counts<<<tiles, BLOCK, 0, c->stream>>>((const uint32_t*)c->vw_nv.p, np, (unsigned long long*)c->vw_v0.p, d_ticket(c, 0),
                                                  (uint64_t*)c->desc.p);
@@ -1859,12 +1965,53 @@ int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, fl
     c->pf_planned = true;
     return LYON_OK;
 }
+int lyon_cuda_flatten_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, uint64_t* n_out_verbs,
+                                  uint64_t* n_out_points) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
+    if (!c || !b || !n_out_verbs || !n_out_points) return LYON_ERR_INVALID_ARGUMENT;
+    return pf_count_impl(c, b, tol, false, n_out_verbs, n_out_points);
+}
+int lyon_cuda_measure_paths_count(lyon_cuda_ctx* c, const lyon_path_batch* b, float tol, uint64_t* n_edges) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_NONE);
+    if (!c || !b || !n_edges) return LYON_ERR_INVALID_ARGUMENT;
+    uint64_t n_verbs = 0;
+    // `let tolerance = tolerance.max(1e-4)` (measure.rs:176; f32::max ignores a NaN operand)
+    return pf_count_impl(c, b, tol > 1e-4f ? tol : 1e-4f, true, &n_verbs, n_edges);
+}
+int lyon_cuda_measure_paths_emit(lyon_cuda_ctx* c, float* d_distance, uint32_t* d_event_index, float* d_t,
+                                 uint64_t* d_path_edge_begin, float* d_path_length) {
+    DeviceGuard device_guard(c ? c->device : -1);
+    if (c) drop_plans(c, KEEP_PATH_FLATTEN);
+    if (!c || !d_path_edge_begin) return LYON_ERR_INVALID_ARGUMENT;
+    if (!c->pf_planned || !c->pf_measure) {
+        c->err = "lyon_cuda_measure_paths_emit without a successful lyon_cuda_measure_paths_count";
+        return LYON_ERR_INVALID_ARGUMENT;
+    }
+    const lyon_path_batch& b = c->pf_batch;
+    if (b.n_paths == 0 || b.n_verbs == 0) {
+        CU_TRY(c, cudaMemsetAsync(d_path_edge_begin, 0, 8ull * ((size_t)b.n_paths + 1), c->stream));
+        if (d_path_length && b.n_paths) CU_TRY(c, cudaMemsetAsync(d_path_length, 0, 4ull * (size_t)b.n_paths, c->stream));
+        return LYON_OK;
+    }
+    if (!d_distance || !d_event_index || !d_t || !d_path_length) return LYON_ERR_INVALID_ARGUMENT;
+    unsigned blocks = (b.n_paths + 7u) / 8u;
+    if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
+    k_pm_emit<<<blocks, 256, 0, c->stream>>>(b.verbs, reinterpret_cast<const V2*>(b.points), b.path_verb_begin, b.n_paths,
+                                            (b.num_attributes + 1u) / 2u, (const PfRec*)c->pf_rec.p,
+                                            (const unsigned long long*)c->vw_t0.p, d_distance, d_event_index, d_t,
+                                            reinterpret_cast<unsigned long long*>(d_path_edge_begin), d_path_length);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return LYON_OK;
+}
 int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* c, uint8_t* d_out_verbs, float* d_out_points, uint32_t* d_out_path_verb_begin,
                                  uint32_t* d_out_path_point_begin) {
     DeviceGuard device_guard(c ? c->device : -1);
     if (c) drop_plans(c, KEEP_PATH_FLATTEN);
     if (!c || !d_out_path_verb_begin || !d_out_path_point_begin) return LYON_ERR_INVALID_ARGUMENT;
-    if (!c->pf_planned) {
+    if (!c->pf_planned || c->pf_measure) {
         c->err = "lyon_cuda_flatten_paths_emit without a successful lyon_cuda_flatten_paths_count";
         return LYON_ERR_INVALID_ARGUMENT;
     }
@@ -1878,7 +2025,8 @@ int lyon_cuda_flatten_paths_emit(lyon_cuda_ctx* c, uint8_t* d_out_verbs, float* 
     unsigned blocks = (b.n_paths + 7u) / 8u;
     if (blocks > (unsigned)c->num_sms * 16u) blocks = (unsigned)c->num_sms * 16u;
     k_pf_emit<<<blocks, 256, 0, c->stream>>>(b.verbs, reinterpret_cast<const V2*>(b.points), b.path_verb_begin, b.path_point_begin,
-                                            b.n_paths, (const PfRec*)c->pf_rec.p, (const unsigned long long*)c->vw_v0.p,
+                                            b.n_paths, b.num_attributes, (const PfRec*)c->pf_rec.p,
+                                            (const unsigned long long*)c->vw_v0.p,
                                             (const unsigned long long*)c->vw_t0.p, d_out_verbs, reinterpret_cast<V2*>(d_out_points),
                                             d_out_path_verb_begin, d_out_path_point_begin);
     c->launches++;

@@ -298,7 +298,7 @@ class DeviceTessellator:
         if st != 0:
             _raise(self.L, self.ctx, st)
         out = DeviceBatch.__new__(DeviceBatch)
-        out.n_paths, out.num_attributes = dbatch.n_paths, 0
+        out.n_paths, out.num_attributes = dbatch.n_paths, dbatch.num_attributes
         out.n_verbs, out.n_points = int(nv.value), int(npt.value)
         out.verbs = torch.empty((out.n_verbs,), dtype=torch.uint8, device=self.device)
         out.points = torch.empty((2 * out.n_points,), dtype=torch.float32, device=self.device)
@@ -309,6 +309,27 @@ class DeviceTessellator:
         if st != 0:
             _raise(self.L, self.ctx, st)
         return out
+
+    def measure_paths(self, dbatch: DeviceBatch, tolerance: float):
+        """`PathMeasurements::from_path(path, tolerance)` for every path of the batch (lyon_cuda_measure_paths_*).
+        Returns (distance f32[E], event_index i32[E], t f32[E], path_edge_begin i64[N + 1], path_length f32[N])."""
+        torch = self.torch
+        ne = ctypes.c_uint64()
+        cb = dbatch.c_struct()
+        st = self.L.lyon_cuda_measure_paths_count(self.ctx, ctypes.byref(cb), tolerance, ctypes.byref(ne))
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        n = int(ne.value)
+        dist = torch.empty((n,), dtype=torch.float32, device=self.device)
+        idx = torch.empty((n,), dtype=torch.int32, device=self.device)
+        t = torch.empty((n,), dtype=torch.float32, device=self.device)
+        begin = torch.empty((dbatch.n_paths + 1,), dtype=torch.int64, device=self.device)
+        length = torch.empty((dbatch.n_paths,), dtype=torch.float32, device=self.device)
+        st = self.L.lyon_cuda_measure_paths_emit(self.ctx, dist.data_ptr(), idx.data_ptr(), t.data_ptr(), begin.data_ptr(),
+                                                 length.data_ptr())
+        if st != 0:
+            _raise(self.L, self.ctx, st)
+        return dist, idx, t, begin, length
 
     def flatten_curves_fused(self, d_ctrl, npts: int, tolerance: float, with_t: bool = False):
         """Single pass (count + scan + emit in one kernel) into buffers kept across calls; they grow when the batch

@@ -214,61 +214,88 @@ double oracle_flatten_cubics_timed(const float* ctrl, uint64_t n, float tol, int
 // the line_to sequence of its flattened points; Begin/Line/End/Close pass through.  Works on paths
 // WITHOUT custom attributes.  Output verbs/points use the same encoding as the input.
 // out arrays must be large enough (call once with NULL outputs to get the sizes).
-void oracle_flatten_paths(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
-                          const uint32_t* path_point_begin, uint32_t n_paths, float tol, uint8_t* out_verbs,
-                          float* out_points, uint32_t* out_path_verb_begin, uint32_t* out_path_point_begin,
-                          uint64_t* n_out_verbs, uint64_t* n_out_points) {
+// Path-level flattening with custom attributes: the `Flattened` builder adapter's helpers (crates/path/src/private.rs:56-122,
+// flatten_quadratic_bezier / flatten_cubic_bezier): every flattened point of a curve carries
+// prev_attributes[i] * (1 - t) + attributes[i] * t, the curve's own attributes where t == 1.0; the other verbs pass through
+// with their attributes.  Attributes are stored two per point slot after every endpoint (path.rs:650-665), an odd
+// count padded with 0.
+void oracle_flatten_paths_attr(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                               const uint32_t* path_point_begin, uint32_t n_paths, uint32_t num_attributes, float tol,
+                               uint8_t* out_verbs, float* out_points, uint32_t* out_path_verb_begin,
+                               uint32_t* out_path_point_begin, uint64_t* n_out_verbs, uint64_t* n_out_points) {
     uint64_t ov = 0, op = 0;
+    const uint32_t A = num_attributes, stride = (A + 1u) / 2u;
+    std::vector<float> buf(2 * (size_t)stride + 2, 0.0f);
     for (uint32_t p = 0; p < n_paths; ++p) {
         if (out_path_verb_begin) out_path_verb_begin[p] = (uint32_t)ov;
         if (out_path_point_begin) out_path_point_begin[p] = (uint32_t)op;
         const float* pts = points + 2 * (size_t)path_point_begin[p];
         uint32_t cur = 0;
         V2 current = v2(0, 0), first = v2(0, 0);
+        const float* cur_attr = nullptr;    // attributes of the current endpoint
+        const float* first_attr = nullptr;  // attributes of the sub-path's first endpoint
         auto P = [&](uint32_t i) { return v2(pts[2 * i], pts[2 * i + 1]); };
-        auto emit = [&](uint8_t verb, bool has_pt, V2 pt) {
+        auto emit = [&](uint8_t verb, bool has_pt, V2 pt, const float* attr) {
             if (out_verbs) out_verbs[ov] = verb;
             ov++;
             if (has_pt) {
                 if (out_points) {
                     out_points[2 * op] = pt.x;
                     out_points[2 * op + 1] = pt.y;
+                    for (uint32_t i = 0; i < 2 * stride; ++i) out_points[2 * (op + 1) + i] = i < A ? attr[i] : 0.0f;
                 }
-                op++;
+                op += 1 + stride;
             }
+        };
+        auto lerp_attr = [&](const float* prev, const float* attr, float t) -> const float* {
+            if (t == 1.0f) return attr;
+            for (uint32_t i = 0; i < A; ++i) buf[i] = prev[i] * (1.0f - t) + attr[i] * t;
+            return buf.data();
         };
         for (uint32_t vi = path_verb_begin[p]; vi < path_verb_begin[p + 1]; ++vi) {
             switch (verbs[vi]) {
                 case 3:
-                    current = first = P(cur++);
-                    emit(3, true, current);
+                    current = first = P(cur);
+                    cur_attr = first_attr = pts + 2 * (size_t)(cur + 1);
+                    cur += 1 + stride;
+                    emit(3, true, current, cur_attr);
                     break;
                 case 0:
-                    current = P(cur++);
-                    emit(0, true, current);
+                    current = P(cur);
+                    cur_attr = pts + 2 * (size_t)(cur + 1);
+                    cur += 1 + stride;
+                    emit(0, true, current, cur_attr);
                     break;
                 case 1: {
                     V2 c = P(cur), to = P(cur + 1);
-                    cur += 2;
-                    quad_for_each_flattened_with_t(current, c, to, tol, [&](V2 q, float) { emit(0, true, q); });
+                    const float* attr = pts + 2 * (size_t)(cur + 2);
+                    const float* prev = cur_attr;
+                    cur += 2 + stride;
+                    quad_for_each_flattened_with_t(current, c, to, tol, [&](V2 q, float t) { emit(0, true, q, lerp_attr(prev, attr, t)); });
                     current = to;
+                    cur_attr = attr;
                     break;
                 }
                 case 2: {
                     V2 c1 = P(cur), c2 = P(cur + 1), to = P(cur + 2);
-                    cur += 3;
-                    cubic_for_each_flattened_with_t(current, c1, c2, to, tol, [&](V2 q, float) { emit(0, true, q); });
+                    const float* attr = pts + 2 * (size_t)(cur + 3);
+                    const float* prev = cur_attr;
+                    cur += 3 + stride;
+                    cubic_for_each_flattened_with_t(current, c1, c2, to, tol, [&](V2 q, float t) { emit(0, true, q, lerp_attr(prev, attr, t)); });
                     current = to;
+                    cur_attr = attr;
                     break;
                 }
                 case 4:
-                    cur += 1;
-                    emit(4, true, first);
+                    cur += 1 + stride;
+                    emit(4, true, first, first_attr);
                     current = first;
+                    cur_attr = first_attr;
                     break;
                 case 5:
-                    emit(5, false, first);
+                    emit(5, false, first, nullptr);
                     current = first;
+                    cur_attr = first_attr;
                     break;
             }
         }
@@ -277,6 +304,93 @@ void oracle_flatten_paths(const uint8_t* verbs, const float* points, const uint3
     if (out_path_point_begin) out_path_point_begin[n_paths] = (uint32_t)op;
     *n_out_verbs = ov;
     *n_out_points = op;
+}
+void oracle_flatten_paths(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                          const uint32_t* path_point_begin, uint32_t n_paths, float tol, uint8_t* out_verbs,
+                          float* out_points, uint32_t* out_path_verb_begin, uint32_t* out_path_point_begin,
+                          uint64_t* n_out_verbs, uint64_t* n_out_points) {
+    oracle_flatten_paths_attr(verbs, points, path_verb_begin, path_point_begin, n_paths, 0u, tol, out_verbs, out_points,
+                              out_path_verb_begin, out_path_point_begin, n_out_verbs, n_out_points);
+}
+
+// PathMeasurements::initialize (crates/algorithms/src/measure.rs:170-257): the edges of every path of a batch.  Pass null
+// outputs to count.  distance / index / t: one entry per edge; path_edge_begin: n_paths + 1; path_length: n_paths.
+void oracle_measure_paths(const uint8_t* verbs, const float* points, const uint32_t* path_verb_begin,
+                          const uint32_t* path_point_begin, uint32_t n_paths, uint32_t num_attributes, float tolerance,
+                          float* distance_out, uint32_t* index_out, float* t_out, uint64_t* path_edge_begin, float* path_length,
+                          uint64_t* n_edges) {
+    const float tol = tolerance > 1e-4f ? tolerance : 1e-4f;  // tolerance.max(1e-4)
+    const uint32_t stride = (num_attributes + 1u) / 2u;
+    uint64_t ne = 0;
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        if (path_edge_begin) path_edge_begin[p] = ne;
+        const float* pts = points + 2 * (size_t)path_point_begin[p];
+        uint32_t cur = 0, index = 0;
+        V2 current = v2(0, 0), first = v2(0, 0);
+        float distance = 0.0f;
+        auto P = [&](uint32_t i) { return v2(pts[2 * i], pts[2 * i + 1]); };
+        auto push = [&](float t) {
+            if (distance_out) {
+                distance_out[ne] = distance;
+                index_out[ne] = index;
+                t_out[ne] = t;
+            }
+            ne++;
+        };
+        for (uint32_t vi = path_verb_begin[p]; vi < path_verb_begin[p + 1]; ++vi, ++index) {
+            switch (verbs[vi]) {
+                case 3:  // Begin
+                    current = first = P(cur);
+                    cur += 1 + stride;
+                    push(1.0f);
+                    break;
+                case 0: {  // Line: distance += (from - to).length()
+                    V2 to = P(cur);
+                    cur += 1 + stride;
+                    distance = distance + length(current - to);
+                    current = to;
+                    push(1.0f);
+                    break;
+                }
+                case 1: {
+                    V2 c = P(cur), to = P(cur + 1);
+                    cur += 2 + stride;
+                    V2 prev = current;
+                    quad_for_each_flattened_with_t(current, c, to, tol, [&](V2 q, float t) {
+                        distance = distance + length(q - prev);  // line.length() = (to - from).length()
+                        prev = q;
+                        push(t);
+                    });
+                    current = to;
+                    break;
+                }
+                case 2: {
+                    V2 c1 = P(cur), c2 = P(cur + 1), to = P(cur + 2);
+                    cur += 3 + stride;
+                    V2 prev = current;
+                    cubic_for_each_flattened_with_t(current, c1, c2, to, tol, [&](V2 q, float t) {
+                        distance = distance + length(q - prev);
+                        prev = q;
+                        push(t);
+                    });
+                    current = to;
+                    break;
+                }
+                case 4:  // End { close: true }: distance += (last - first).length()
+                    cur += 1 + stride;
+                    distance = distance + length(current - first);
+                    current = first;
+                    push(1.0f);
+                    break;
+                case 5:  // End { close: false }: no edge
+                    current = first;
+                    break;
+            }
+        }
+        if (path_length) path_length[p] = distance;
+    }
+    if (path_edge_begin) path_edge_begin[n_paths] = ne;
+    *n_edges = ne;
 }
 
 // ---- small pure functions exposed for known-answer tests ----------------------------------------

@@ -94,6 +94,10 @@ extern "C" {
                                          n_out_verbs: *mut u64, n_out_points: *mut u64) -> c_int;
     pub fn lyon_cuda_flatten_paths_emit(ctx: *mut lyon_cuda_ctx, d_out_verbs: *mut u8, d_out_points: *mut f32,
                                         d_out_path_verb_begin: *mut u32, d_out_path_point_begin: *mut u32) -> c_int;
+    pub fn lyon_cuda_measure_paths_count(ctx: *mut lyon_cuda_ctx, d_batch: *const lyon_path_batch, tolerance: f32,
+                                         n_edges: *mut u64) -> c_int;
+    pub fn lyon_cuda_measure_paths_emit(ctx: *mut lyon_cuda_ctx, d_distance: *mut f32, d_event_index: *mut u32, d_t: *mut f32,
+                                        d_path_edge_begin: *mut u64, d_path_length: *mut f32) -> c_int;
     pub fn lyon_cuda_rebase_indices(ctx: *mut lyon_cuda_ctx, d_indices: *mut u32, n_indices: u64, n_vertices: u64,
                                     vertex_base: u64) -> c_int;
     pub fn lyon_cuda_interpolate_attributes(ctx: *mut lyon_cuda_ctx, d_batch: *const lyon_path_batch,

@@ -49,6 +49,10 @@ def lib():
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.oracle_flatten_paths.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_float] + \
             [ctypes.c_void_p] * 4 + [ctypes.POINTER(ctypes.c_uint64)] * 2
+        L.oracle_flatten_paths_attr.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float] + \
+            [ctypes.c_void_p] * 4 + [ctypes.POINTER(ctypes.c_uint64)] * 2
+        L.oracle_measure_paths.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float] + \
+            [ctypes.c_void_p] * 5 + [ctypes.POINTER(ctypes.c_uint64)]
         L.oracle_compute_normal.argtypes = [ctypes.c_float] * 4 + [ctypes.c_void_p]
         L.oracle_fast_atan2.restype = ctypes.c_float
         L.oracle_fast_atan2.argtypes = [ctypes.c_float] * 2
@@ -164,22 +168,43 @@ def flatten_cubics_timed(ctrl: np.ndarray, tol: float, n_threads: int):
 
 
 def flatten_paths(batch: PathBatch, tol: float) -> PathBatch:
-    assert batch.num_attributes == 0
+    """Path-level flattening (iterator.rs:125-226; with custom attributes: private.rs:56-122)."""
     L = lib()
     verbs = np.ascontiguousarray(batch.verbs, np.uint8)
     pts = np.ascontiguousarray(batch.points, np.float32)
     vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32)
     pb = np.ascontiguousarray(batch.path_point_begin, np.uint32)
+    na = int(batch.num_attributes)
     nv, npnt = ctypes.c_uint64(0), ctypes.c_uint64(0)
-    L.oracle_flatten_paths(_p(verbs), _p(pts), _p(vb), _p(pb), batch.n_paths, tol, None, None, None, None,
-                           ctypes.byref(nv), ctypes.byref(npnt))
+    L.oracle_flatten_paths_attr(_p(verbs), _p(pts), _p(vb), _p(pb), batch.n_paths, na, ctypes.c_float(tol), None, None, None, None,
+                                ctypes.byref(nv), ctypes.byref(npnt))
     ov = np.zeros(nv.value, np.uint8)
     op = np.zeros((npnt.value, 2), np.float32)
     ovb = np.zeros(batch.n_paths + 1, np.uint32)
     opb = np.zeros(batch.n_paths + 1, np.uint32)
-    L.oracle_flatten_paths(_p(verbs), _p(pts), _p(vb), _p(pb), batch.n_paths, tol, _p(ov), _p(op), _p(ovb), _p(opb),
-                           ctypes.byref(nv), ctypes.byref(npnt))
-    return PathBatch(ov, op, ovb, opb, 0)
+    L.oracle_flatten_paths_attr(_p(verbs), _p(pts), _p(vb), _p(pb), batch.n_paths, na, ctypes.c_float(tol), _p(ov), _p(op), _p(ovb),
+                                _p(opb), ctypes.byref(nv), ctypes.byref(npnt))
+    return PathBatch(ov, op, ovb, opb, na)
+
+
+def measure_paths(batch: PathBatch, tol: float):
+    """PathMeasurements::from_path for every path (measure.rs:140-260): (distance, event_index, t, path_edge_begin,
+    path_length)."""
+    L = lib()
+    verbs = np.ascontiguousarray(batch.verbs, np.uint8)
+    pts = np.ascontiguousarray(batch.points, np.float32)
+    vb = np.ascontiguousarray(batch.path_verb_begin, np.uint32)
+    pb = np.ascontiguousarray(batch.path_point_begin, np.uint32)
+    ne = ctypes.c_uint64(0)
+    args = (_p(verbs), _p(pts), _p(vb), _p(pb), batch.n_paths, int(batch.num_attributes), ctypes.c_float(tol))
+    L.oracle_measure_paths(*args, None, None, None, None, None, ctypes.byref(ne))
+    dist = np.zeros(ne.value, np.float32)
+    idx = np.zeros(ne.value, np.uint32)
+    t = np.zeros(ne.value, np.float32)
+    begin = np.zeros(batch.n_paths + 1, np.uint64)
+    length = np.zeros(batch.n_paths, np.float32)
+    L.oracle_measure_paths(*args, _p(dist), _p(idx), _p(t), _p(begin), _p(length), ctypes.byref(ne))
+    return dist, idx, t, begin, length
 
 
 def compute_normal(v1, v2):

@@ -280,6 +280,60 @@ def test_flatten_paths(tz, route):
     assert_mesh_parity(device_mesh_to_host(v, i), O.stroke_batch(O.flatten_paths(batch, 0.1), o), bbox_extent(batch))
 
 
+def test_flatten_paths_with_attributes(tz, route):
+    """Path-level flattening of paths that carry custom attributes (crates/path/src/private.rs:56-122): byte-identical to
+    the oracle for 1, 2 and 3 attributes (odd counts are padded), incl. the reference's `flattened_custom_attributes`
+    path (path.rs:2106-2142); and the flattened batch strokes with a variable line width like the oracle's."""
+    if route != "tile":
+        pytest.skip("one route")
+    import torch
+    b = Path.builder_with_attributes(1)
+    b.begin((0.0, 0.0), [0.0])
+    b.quadratic_bezier_to((1.0, 0.0), (1.0, 1.0), [1.0])
+    b.cubic_bezier_to((1.0, 2.0), (0.0, 2.0), (0.0, 1.0), [2.0])
+    b.end(False)
+    batches = [(PathBatch.from_paths([b.build()]), 0.01)]
+    for na in (1, 2, 3):
+        batches.append((W.random_width_paths(300, seed=40 + na, num_attributes=na), 0.05))
+    for batch, tol in batches:
+        out = tz.flatten_paths(tz.upload(batch), tol)
+        torch.cuda.synchronize()
+        want = O.flatten_paths(batch, tol)
+        assert out.num_attributes == batch.num_attributes
+        assert np.array_equal(out.verbs.cpu().numpy(), want.verbs)
+        assert out.points.cpu().numpy().tobytes() == np.ascontiguousarray(want.points, np.float32).tobytes()
+        assert np.array_equal(out.path_verb_begin.cpu().numpy().astype(np.uint32), want.path_verb_begin)
+        assert np.array_equal(out.path_point_begin.cpu().numpy().astype(np.uint32), want.path_point_begin)
+    # a flattened batch with attributes is a batch: variable line width on the device and with the oracle
+    batch = W.random_width_paths(200, seed=77, num_attributes=1)
+    out = tz.flatten_paths(tz.upload(batch), 0.05)
+    o = StrokeOptions(line_join=LineJoin.Miter).with_variable_line_width(0)
+    v, i = tz.stroke(out, o)
+    torch.cuda.synchronize()
+    from lyon_b200 import device_mesh_to_host
+    assert np.array_equal(device_mesh_to_host(v, i).indices, O.stroke_batch(O.flatten_paths(batch, 0.05), o).indices)
+
+
+def test_measure_paths(tz, route):
+    """`PathMeasurements::from_path` on the device (lyon_cuda_measure_paths_*, a consumer of flattening: measure.rs:140-260)
+    against the oracle: the same edges, byte for byte -- the f32 running distance is replayed in event order."""
+    if route != "tile":
+        pytest.skip("one route")
+    import torch
+    for batch in (W.random_small_paths(400, 33, degenerate=0.1), W.c3_mixed_paths(1500, 64, seed=6, closed_fraction=0.3),
+                  W.random_width_paths(200, seed=51, num_attributes=3), PathBatch.from_paths(W.fixture_paths(GOLDEN)),
+                  PathBatch.from_paths([Path.builder().build()])):
+        for tol in (0.25, 0.01, 1e-6):
+            got = tz.measure_paths(tz.upload(batch), tol)
+            torch.cuda.synchronize()
+            want = O.measure_paths(batch, tol)
+            assert np.array_equal(got[3].cpu().numpy().astype(np.uint64), want[3])
+            assert got[0].cpu().numpy().tobytes() == want[0].tobytes(), "distance"
+            assert np.array_equal(got[1].cpu().numpy().astype(np.uint32), want[1]), "event index"
+            assert got[2].cpu().numpy().tobytes() == want[2].tobytes(), "t"
+            assert got[4].cpu().numpy().tobytes() == want[4].tobytes(), "path length"
+
+
 def test_rebase_indices(tz, route):
     """lyon_cuda_rebase_indices: a mesh emitted with local ids, rebased afterwards == emitted with the base (the
     multi-GPU single-pass flow), for every alignment of the index buffer."""

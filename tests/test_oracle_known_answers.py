@@ -263,3 +263,85 @@ def test_rust_logo_fixture_shape():  # 10 closed sub-paths, 146 cub
     assert np.bincount(path.verbs, minlength=6).tolist() == [89, 0, 146, 10, 10, 0]
     for join in (LineJoin.Miter, LineJoin.Bevel, LineJoin.Round):  # bench/tess stroke_01..03
         check_invariants(path, StrokeOptions(line_join=join), winding=False)
+
+
+def test_flattened_custom_attributes():
+    """crates/path/src/path.rs:2106-2142 `flattened_custom_attributes`: along the flattened events of a path whose
+    endpoints carry the attribute 0, 1, 2 the attribute strictly increases, every Line starts from the previous value, and
+    no curve survives.  Run on the oracle's attribute-aware path flattening (private.rs:56-122)."""
+    from lyon_b200.path import Path, PathBatch, LINE_TO, BEGIN, END
+    b = Path.builder_with_attributes(1)
+    b.begin((0.0, 0.0), [0.0])
+    b.quadratic_bezier_to((1.0, 0.0), (1.0, 1.0), [1.0])
+    b.cubic_bezier_to((1.0, 2.0), (0.0, 2.0), (0.0, 1.0), [2.0])
+    b.end(False)
+    flat = O.flatten_paths(PathBatch.from_paths([b.build()]), 0.01).path(0)
+    assert set(flat.verbs.tolist()) == {LINE_TO, BEGIN, END}
+    prev = -1.0
+    n_lines = 0
+    for ev in flat.iter_with_attributes():
+        if ev[0] == "begin":
+            attr = ev[1][1][0]
+        elif ev[0] == "line":
+            assert ev[1][1][0] == prev
+            attr = ev[2][1][0]
+            n_lines += 1
+        else:
+            assert ev[0] == "end" and ev[1][1][0] == prev
+            continue
+        assert attr > prev
+        prev = attr
+    assert n_lines > 10 and prev == 2.0
+    # the attribute of every flattened point is prev * (1 - t) + attr * t for the accumulated t of for_each_flattened_with_t
+    ctrl = np.array([[0, 0, 1, 0, 1, 1]], np.float32)
+    _off, _pts, t = O.flatten_quadratics(ctrl, 0.01, with_t=True)
+    got = [e[2][1][0] for e in flat.iter_with_attributes() if e[0] == "line"][: len(t)]
+    want = [np.float32(1.0) if ti == 1.0 else np.float32(np.float32(0.0) * (np.float32(1.0) - ti) + np.float32(1.0) * ti) for ti in t]
+    assert got == want
+
+
+def test_path_measurements_known_answers():
+    """The measurements behind crates/algorithms/src/measure.rs `measure_line` (:718-733), `measure_square` (:735-756: the
+    normalized samples 0.125 / 0.375 / ... fall on the edge midpoints, i.e. the closed unit square measures 4 with an edge
+    at every unit) and `measure_bezier_curve` (:782-806: half of the length is reached at the joint of two mirrored
+    quadratics), plus the edge layout of `PathMeasurements::initialize` (:170-257): every Begin / Line / Close contributes
+    one edge with t = 1, an open End none."""
+    from lyon_b200.path import Path, PathBatch
+    b = Path.builder()
+    b.begin((0.0, 0.0))
+    b.line_to((1.0, 0.0))
+    b.end(False)
+    line = b.build()
+    b = Path.builder()
+    b.begin((0.0, 0.0))
+    b.line_to((1.0, 0.0))
+    b.line_to((1.0, 1.0))
+    b.line_to((0.0, 1.0))
+    b.close()
+    square = b.build()
+    dist, idx, t, begin, length = O.measure_paths(PathBatch.from_paths([line, square]), 0.01)
+    assert begin.tolist() == [0, 2, 7]
+    assert length.tolist() == [1.0, 4.0]
+    assert dist.tolist() == [0.0, 1.0, 0.0, 1.0, 2.0, 3.0, 4.0]
+    assert idx.tolist() == [0, 1, 0, 1, 2, 3, 4] and set(t.tolist()) == {1.0}
+    # a curve: one edge per flattened segment, t = the accumulated parameter, the last one exactly 1; the length is the
+    # polyline's (measure.rs:`measure_bezier_curve` checks the quarter-circle-like quadratic (0,0)-(0.5,0.7)-(1,0) ~ 1.68)
+    b = Path.builder()
+    b.begin((0.0, 0.0))
+    b.quadratic_bezier_to((0.5, 0.7), (1.0, 0.0))
+    b.end(False)
+    q = PathBatch.from_paths([b.build()])
+    dist, idx, t, begin, length = O.measure_paths(q, 0.01)
+    off, pts, tt = O.flatten_quadratics(np.array([[0, 0, 0.5, 0.7, 1, 0]], np.float32), 0.01, with_t=True)
+    assert len(dist) == 1 + len(pts) and t[1:].tolist() == tt.tolist() and t[-1] == 1.0
+    assert np.all(np.diff(dist) > 0) and abs(float(length[0]) - 1.4) < 0.2
+    b = Path.builder()
+    b.begin((0.0, 0.0))
+    b.quadratic_bezier_to((0.5, 0.7), (1.0, 0.0))
+    b.quadratic_bezier_to((1.5, -0.7), (2.0, 0.0))
+    b.end(False)
+    d2, i2, t2, _b2, l2 = O.measure_paths(PathBatch.from_paths([b.build()]), 0.01)
+    joint = d2[np.flatnonzero((i2 == 1) & (t2 == 1.0))[0]]
+    assert abs(float(joint) / float(l2[0]) - 0.5) < 1e-5
+    # tolerance.max(1e-4): a tiny tolerance measures like 1e-4
+    assert O.measure_paths(q, 1e-9)[4][0] == O.measure_paths(q, 1e-4)[4][0]
