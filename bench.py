@@ -112,7 +112,8 @@ def cpu_baseline(sample_paths: int, threads: int):
     batch = W.c3_batch_range(0, sample_paths, N_SEGMENTS)
     secs, nv, ni = O.stroke_batch_timed(batch, stroke_options(), threads)
     return {"value": nv / secs, "unit": "vertices/s", "cores": threads, "kind": "port",
-            "sample": f"first {sample_paths} paths of the same C3 batch ({nv} vertices, {secs:.2f} s, warm buffers)"}
+            "sample": f"first {sample_paths} paths of the same C3 batch ({nv} vertices, {secs:.2f} s, warm buffers)",
+            "sample_vertices": int(nv), "sample_indices": int(ni)}
 
 
 def run_reference(args):
@@ -171,6 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flatten", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C4 / C5 sub-benchmarks")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -286,9 +288,11 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "k_stroke_tile<FUSED>", "achieved": k_gbs,
         "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "peak_source": peak_src,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: ncu --set full on the first 200k paths of the same
-        # batch measured 9.647 GB for 8.686 GB of algorithmic bytes (profiles/r01k_ncu_summary.txt); scaled to this launch
-        "traffic": int(alg_bytes * (9.362 / 8.686)), "traffic_source": "ncu capture on a 200k-path sample, scaled by algorithmic bytes",
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: `ncu --set full` on the first 200k paths of the same
+        # batch (profiles/r02_ncu_summary.txt) measured 8.526 GB written + 0.488 GB read = 9.014 GB for 8.686 GB of
+        # algorithmic bytes.  ESTIMATE for this launch: that ratio times the launch's algorithmic bytes (a profiler cannot
+        # run inside the timed region).
+        "traffic": int(alg_bytes * (9.014 / 8.686)), "traffic_source": "estimated: ncu ratio of a 200k-path sample x algorithmic bytes",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms": dev_ms / args.steps,
         "kernel_share_of_step": k_ms / (dev_ms / args.steps),
         "whole_step_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
@@ -328,9 +332,20 @@ def main():
     if world == 1 and not args.no_flatten:
         flatten = bench_flatten(tz, torch, dev, peak, args)
 
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = bench_configs(tz, torch, peak)
+
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
-        cpu = cpu_baseline(min(args.cpu_sample, total_paths), os.cpu_count() or 1)
+        sample = min(args.cpu_sample, total_paths)
+        cpu = cpu_baseline(sample, os.cpu_count() or 1)
+        # the GPU arm on the very same sample must produce the very same totals as the CPU arm
+        gv, gi = tz.stroke_fused(tz.upload(batch.slice(0, sample)), opts)
+        cpu["gpu_same_sample"] = {"vertices": int(gv.shape[0]), "indices": int(gi.shape[0])}
+        assert (int(gv.shape[0]), int(gi.shape[0])) == (cpu["sample_vertices"], cpu["sample_indices"]), \
+            f"GPU and CPU arms disagree on the first {sample} paths: {gv.shape[0]}/{gi.shape[0]} vs {cpu['sample_vertices']}/{cpu['sample_indices']}"
+        del gv, gi
 
     if rank == 0:
         line = {
@@ -338,13 +353,74 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "flatten": flatten,
+            "roofline": roofline, "cpu_baseline": cpu, "flatten": flatten, "configs": configs,
             "output": {"vertices": total_v, "indices": total_i, "bytes": 32 * total_v + 4 * total_i},
             "wall_ms_per_step": 1e3 * t_wall / args.steps, "workspace_bytes": tz.workspace_bytes(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_fused(tz, torch, d, o, reps=3):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    best = None
+    for _ in range(reps + 1):
+        ev[0].record()
+        v, i = tz.stroke_fused(d, o)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1])
+        best = ms if best is None else min(best, ms)
+    tz.check()
+    return best, int(v.shape[0]), int(i.shape[0])
+
+
+def bench_configs(tz, torch, peak):
+    """The other configs of BASELINE.json on one GPU (device-resident inputs, whole lyon_cuda_stroke_fused call incl. its
+    pre-pass): C4 = 100k polylines x 1k segments, miter limit 4, butt caps, fixed and variable line width; C5 = the two
+    logo fixtures x 1000 jittered copies, tolerance sweep 1.0 .. 0.001; and the host-side packing rate of
+    PathBatch.from_paths."""
+    import workloads as W
+    from lyon_b200 import LineJoin, PathBatch, StrokeOptions
+    out = {}
+    o4 = StrokeOptions(line_join=LineJoin.Miter, miter_limit=4.0)
+    for vw in (False, True):
+        batch = W.c4_polylines(100_000, 1000, with_attribute=vw)
+        d = tz.upload(batch)
+        ms, nv, ni = _time_fused(tz, torch, d, o4.with_variable_line_width(0) if vw else o4)
+        alg = d.input_bytes() + 32 * nv + 4 * ni
+        out["C4_variable_width" if vw else "C4_fixed_width"] = {
+            "workload": "100k polylines x 1k segments, miter joins (limit 4), butt caps" + (", width attribute 0" if vw else ""),
+            "ms": ms, "vertices": nv, "indices": ni, "value": nv / (ms * 1e-3), "unit": "vertices/s",
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg, "scope": "whole call"}}
+        del d, batch
+        tz._own_v = tz._own_i = None
+        torch.cuda.empty_cache()
+    paths = W.fixture_paths(ROOT / "tests" / "golden")
+    t0 = time.perf_counter()
+    batch = W.c5_logo_copies(paths, 1000)
+    d = tz.upload(batch)
+    sweep = []
+    for tol in (1.0, 0.1, 0.01, 0.003, 0.001):
+        ms, nv, ni = _time_fused(tz, torch, d, StrokeOptions(tolerance=tol))
+        alg = d.input_bytes() + 32 * nv + 4 * ni
+        sweep.append({"tolerance": tol, "ms": ms, "vertices": nv, "indices": ni, "value": nv / (ms * 1e-3),
+                      "frac": alg / (ms * 1e-3) / 1e9 / peak})
+    out["C5_tolerance_sweep"] = {"workload": "logo.path + rust_logo.path x 1000 jittered copies, width 1, miter, butt",
+                                 "unit": "vertices/s", "sweep": sweep}
+    # packing: lyon Paths -> the SoA batch the device reads (host side of the boundary, SURVEY 8 f1)
+    plist = [batch.path(i) for i in range(min(batch.n_paths, 2000))]
+    t0 = time.perf_counter()
+    PathBatch.from_paths(plist)
+    dt = time.perf_counter() - t0
+    out["packing"] = {"api": "PathBatch.from_paths (numpy concatenation)", "paths": len(plist), "paths_per_s": len(plist) / dt,
+                      "verbs_per_s": float(sum(p.verbs.shape[0] for p in plist)) / dt}
+    del d
+    tz._own_v = tz._own_i = None
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_flatten(tz, torch, dev, peak, args):

@@ -8,13 +8,15 @@ from .geometry import STROKE_VERTEX_DTYPE, TessellationError, TooManyVertices, V
 from .options import LineCap, LineJoin, StrokeOptions
 from .path import Path, PathBatch, PathBuilder, SvgPathBuilder, parse_svg_path
 from .sharding import ShardedStroker, exchange_totals, partition_by_cost
-from .tessellator import (DeviceBatch, DeviceTessellator, HostPipeline, StrokeTessellator, device_mesh_to_host, flatten_cubics,
-                          flatten_quadratics, tessellate_paths)
+from .shapes import StrokeBuilder, StrokeTessellator
+from .tessellator import (DeviceBatch, DeviceTessellator, HostPipeline, device_mesh_to_host, flatten_cubics, flatten_quadratics,
+                          tessellate_paths)
 
 __all__ = [
     "Path", "PathBatch", "PathBuilder", "SvgPathBuilder", "parse_svg_path",
     "LineCap", "LineJoin", "StrokeOptions",
     "VertexBuffers", "STROKE_VERTEX_DTYPE", "TessellationError", "TooManyVertices",
-    "DeviceBatch", "DeviceTessellator", "HostPipeline", "StrokeTessellator", "tessellate_paths", "device_mesh_to_host",
+    "DeviceBatch", "DeviceTessellator", "HostPipeline", "StrokeTessellator", "StrokeBuilder", "tessellate_paths",
+    "device_mesh_to_host",
     "flatten_cubics", "flatten_quadratics", "ShardedStroker", "exchange_totals", "partition_by_cost",
 ]

@@ -39,6 +39,10 @@ class VertexBuffers:
     vertices: np.ndarray  # STROKE_VERTEX_DTYPE [V]
     indices: np.ndarray  # uint32 [I]
 
+    @staticmethod
+    def empty() -> "VertexBuffers":
+        return VertexBuffers(np.zeros(0, STROKE_VERTEX_DTYPE), np.zeros(0, np.uint32))
+
     def positions(self) -> np.ndarray:
         """StrokeVertex::position() = position_on_path + normal * half_width (stroke.rs:2676-2678), in f32."""
         v = self.vertices

@@ -421,18 +421,6 @@ def tessellate_paths(paths: Union[PathBatch, Iterable[Path]], options: StrokeOpt
     return VertexBuffers(v, i)
 
 
-class StrokeTessellator:
-    """`lyon_tessellation::StrokeTessellator` (stroke.rs:108-308) for single paths."""
-
-    def __init__(self, tessellator: Optional[DeviceTessellator] = None):
-        self._tz = tessellator
-
-    def tessellate_path(self, path: Path, options: StrokeOptions) -> VertexBuffers:
-        return tessellate_paths([path], options, self._tz)
-
-    tessellate = tessellate_path
-
-
 def device_mesh_to_host(vertices, indices) -> VertexBuffers:
     """Device tensors of DeviceTessellator.stroke_emit -> host VertexBuffers."""
     v = vertices.cpu().numpy().view(STROKE_VERTEX_DTYPE).reshape(-1)

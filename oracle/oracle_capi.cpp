@@ -393,6 +393,156 @@ void oracle_measure_paths(const uint8_t* verbs, const float* points, const uint3
     *n_edges = ne;
 }
 
+// ---- shape helpers of the path builders (crates/path/src/builder.rs:555-700, 1506-1660) and StrokeBuilder::add_rectangle's
+// thin-rectangle rule (crates/tessellation/src/stroke.rs:523-537, 2336-2369), restated for the host-side generators of
+// lyon_b200/shapes.py.  A shape is returned as lyon Path storage: verbs + points (no attributes).
+namespace {
+struct ShapeOut {
+    uint8_t* verbs;
+    float* points;
+    uint32_t nv = 0, np = 0;
+    void pt(V2 p) {
+        if (points) {
+            points[2 * np] = p.x;
+            points[2 * np + 1] = p.y;
+        }
+        np++;
+    }
+    void verb(uint8_t v) {
+        if (verbs) verbs[nv] = v;
+        nv++;
+    }
+    V2 first = v2(0, 0);
+    void begin(V2 p) { first = p; pt(p); verb(3); }
+    void line_to(V2 p) { pt(p); verb(0); }
+    void quad_to(V2 c, V2 p) { pt(c); pt(p); verb(1); }
+    void cubic_to(V2 c1, V2 c2, V2 p) { pt(c1); pt(c2); pt(p); verb(2); }
+    void end(bool close) {
+        if (close) pt(first);
+        verb(close ? 4 : 5);
+    }
+};
+// sample_ellipse (crates/geom/src/arc.rs:745-750): Rotation::new(x_rotation).transform_point(rx cos a, ry sin a)
+V2 shape_sample_ellipse(V2 radii, float x_rotation, float angle) {
+    const float ex = radii.x * libm_cos(angle), ey = radii.y * libm_sin(angle);
+    const float c = libm_cos(x_rotation), s = libm_sin(x_rotation);
+    return v2(ex * c - ey * s, ey * c + ex * s);
+}
+}  // namespace
+
+// kind 0 rectangle (p: min.x min.y max.x max.y), 1 circle (cx cy r), 2 ellipse (cx cy rx ry x_rotation),
+// 3 rounded rectangle (min.x min.y max.x max.y tl tr bl br); winding +1 / -1.  Null outputs count.
+void oracle_shape_path(int kind, const float* p, int winding, uint8_t* verbs, float* points, uint32_t* n_verbs, uint32_t* n_points) {
+    ShapeOut o{verbs, points};
+    const bool positive = winding >= 0;
+    const float dir = positive ? 1.0f : -1.0f;
+    if (kind == 0) {  // builder.rs:649-678
+        const V2 mn = v2(p[0], p[1]), mx = v2(p[2], p[3]);
+        o.begin(mn);
+        if (positive) {
+            o.line_to(v2(mx.x, mn.y));
+            o.line_to(mx);
+            o.line_to(v2(mn.x, mx.y));
+        } else {
+            o.line_to(v2(mn.x, mx.y));
+            o.line_to(mx);
+            o.line_to(v2(mx.x, mn.y));
+        }
+        o.end(true);
+    } else if (kind == 1) {  // builder.rs:1508-1546
+        const V2 c = v2(p[0], p[1]);
+        const float radius = fabsf(p[2]);
+        const float d = radius * 0.55191505f;
+        o.begin(c + v2(-radius, 0.0f));
+        o.cubic_to(c + v2(-radius, -d * dir), c + v2(-d, -radius * dir), c + v2(0.0f, -radius * dir));
+        o.cubic_to(c + v2(d, -radius * dir), c + v2(radius, -d * dir), c + v2(radius, 0.0f));
+        o.cubic_to(c + v2(radius, d * dir), c + v2(d, radius * dir), c + v2(0.0f, radius * dir));
+        o.cubic_to(c + v2(-d, radius * dir), c + v2(-radius, d * dir), c + v2(-radius, 0.0f));
+        o.end(true);
+    } else if (kind == 2) {  // builder.rs:606-636 + arc.rs:668-703 (arc_to_quadratic_beziers_with_t)
+        const V2 c = v2(p[0], p[1]), radii = v2(p[2], p[3]);
+        const float x_rotation = p[4], start_angle = 0.0f;
+        const float sweep_angle = (2.0f * PI_F) * dir;
+        o.begin(c + shape_sample_ellipse(radii, x_rotation, start_angle + sweep_angle * 0.0f));
+        const float sign = sweep_angle < 0.0f ? -1.0f : 1.0f;
+        const float sweep = fminf(fabsf(sweep_angle), PI_F * 2.0f);
+        const float n_steps = ceilf(sweep / (PI_F / 4.0f));
+        const float step = sweep / n_steps * sign;
+        const float alpha = (float)tan((double)(step * 0.5f));
+        const int n = (int)n_steps;
+        const float xc = libm_cos(x_rotation), xs = libm_sin(x_rotation);
+        for (int i = 0; i < n; ++i) {
+            const float a1 = start_angle + step * (float)i, a2 = start_angle + step * (float)(i + 1);
+            const V2 from = c + shape_sample_ellipse(radii, x_rotation, a1);
+            const V2 to = c + shape_sample_ellipse(radii, x_rotation, a2);
+            // Arc::tangent_at_angle (arc.rs:231-243): rotate (-rx sin a, ry cos a) by x_rotation
+            const float tx = -radii.x * libm_sin(a1), ty = radii.y * libm_cos(a1);
+            const V2 tg = v2(tx * xc - ty * xs, ty * xc + tx * xs);
+            o.quad_to(from + tg * alpha, to);
+        }
+        o.end(true);
+    } else if (kind == 3) {  // builder.rs:1551-1660
+        const float x_min = p[0], y_min = p[1], x_max = p[2], y_max = p[3];
+        const float w = x_max - x_min, h = y_max - y_min, min_wh = fminf(w, h);
+        float tl = fminf(fabsf(p[4]), min_wh), tr = fminf(fabsf(p[5]), min_wh), bl = fminf(fabsf(p[6]), min_wh),
+              br = fminf(fabsf(p[7]), min_wh);
+        if (tl + tr > w) { const float x = (tl + tr - w) * 0.5f; tl -= x; tr -= x; }
+        if (bl + br > w) { const float x = (bl + br - w) * 0.5f; bl -= x; br -= x; }
+        if (tr + br > h) { const float x = (tr + br - h) * 0.5f; tr -= x; br -= x; }
+        if (tl + bl > h) { const float x = (tl + bl - h) * 0.5f; tl -= x; bl -= x; }
+        const float K = 0.55191505f;
+        const float tl_d = tl * K, tr_d = tr * K, br_d = br * K, bl_d = bl * K;
+        const V2 tlc = v2(x_min, y_min), trc = v2(x_max, y_min), brc = v2(x_max, y_max), blc = v2(x_min, y_max);
+        const V2 q[16] = {v2(x_min, y_min + tl), tlc + v2(0.0f, tl - tl_d), tlc + v2(tl - tl_d, 0.0f), tlc + v2(tl, 0.0f),
+                          v2(x_max - tr, y_min), trc + v2(-tr + tr_d, 0.0f), trc + v2(0.0f, tr - tr_d), trc + v2(0.0f, tr),
+                          v2(x_max, y_max - br), brc + v2(0.0f, -br + br_d), brc + v2(-br + br_d, 0.0f), brc + v2(-br, 0.0f),
+                          v2(x_min + bl, y_max), blc + v2(bl - bl_d, 0.0f), blc + v2(0.0f, -bl + bl_d), blc + v2(0.0f, -bl)};
+        if (positive) {
+            o.begin(q[0]);
+            if (tl > 0.0f) o.cubic_to(q[1], q[2], q[3]);
+            o.line_to(q[4]);
+            if (tr > 0.0f) o.cubic_to(q[5], q[6], q[7]);
+            o.line_to(q[8]);
+            if (br > 0.0f) o.cubic_to(q[9], q[10], q[11]);
+            o.line_to(q[12]);
+            if (bl > 0.0f) o.cubic_to(q[13], q[14], q[15]);
+        } else {
+            o.begin(q[15]);
+            if (bl > 0.0f) o.cubic_to(q[14], q[13], q[12]);
+            o.line_to(q[11]);
+            if (br > 0.0f) o.cubic_to(q[10], q[9], q[8]);
+            o.line_to(q[7]);
+            if (tr > 0.0f) o.cubic_to(q[6], q[5], q[4]);
+            o.line_to(q[3]);
+            if (tl > 0.0f) o.cubic_to(q[2], q[1], q[0]);
+        }
+        o.end(true);
+    }
+    *n_verbs = o.nv;
+    *n_points = o.np;
+}
+
+// StrokeBuilder::add_rectangle (stroke.rs:523-537) + approximate_thin_rectangle (stroke.rs:2336-2369): returns 1 and the
+// stand-in line segment out[0..3], line width out[4], cap out[5] when the rectangle is approximated; 0 otherwise.
+int oracle_thin_rectangle(const float* rect, float line_width, int line_join, float* out) {
+    const float w = rect[2] - rect[0], h = rect[3] - rect[1];
+    const float threshold = (line_join == 0 ? 1.0f : 0.05f) * line_width;
+    if (!(fabsf(w) < threshold || fabsf(h) < threshold)) return 0;
+    float d;
+    if (w > h) {
+        d = h * 0.5f;
+        const float y = (rect[1] + rect[3]) * 0.5f;
+        out[0] = rect[0] + d; out[1] = y; out[2] = rect[2] - d; out[3] = y;
+    } else {
+        d = w * 0.5f;
+        const float x = (rect[0] + rect[2]) * 0.5f;
+        out[0] = x; out[1] = rect[1] + d; out[2] = x; out[3] = rect[3] - d;
+    }
+    out[4] = line_width + d;
+    out[5] = line_join == 2 ? 2.0f : 1.0f;  // LineJoin::Round -> LineCap::Round, else Square
+    return 1;
+}
+
 // ---- small pure functions exposed for known-answer tests ----------------------------------------
 void oracle_compute_normal(float v1x, float v1y, float v2x, float v2y, float* out) {
     V2 n = compute_normal(v2(v1x, v1y), v2(v2x, v2y));
