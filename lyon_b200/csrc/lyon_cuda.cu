@@ -569,8 +569,12 @@ __global__ void __launch_bounds__(BLOCK) k_flat_count(const float* __restrict__ 
 //                             point is the exact endpoint.  Points go to the window at their output position.
 //   phase B  thread / point   the window leaves the SM as contiguous 8-byte stores (a warp = 256 contiguous bytes).
 // HBM traffic: control points and offsets once, every output point once.
-constexpr int FLAT_CURVES = 256;
-constexpr int FLAT_WINDOW = 8192;    // points per window (4096 when the curve parameters are written too)
+#ifndef LYON_FLAT_CURVES
+#define LYON_FLAT_CURVES 256
+#define LYON_FLAT_WINDOW 8192
+#endif
+constexpr int FLAT_CURVES = LYON_FLAT_CURVES;
+constexpr int FLAT_WINDOW = LYON_FLAT_WINDOW;  // points per window (half of it when the curve parameters are written too)
 template <int NPTS>
 struct FlatSmem {
     unsigned long long off[FLAT_CURVES + 1];
@@ -586,7 +590,7 @@ struct FlatFused {
     uint64_t* desc;
     Totals* totals;
 };
-template <int NPTS, bool FUSED>
+template <int NPTS, bool FUSED, bool WITH_T>
 __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restrict__ ctrl, unsigned long long n, float tol,
                                                            const unsigned long long* __restrict__ offsets,
                                                            float2* __restrict__ out, float* __restrict__ t_out, FlatFused fu) {
@@ -657,36 +661,46 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
         total = sm.off[nc] - base;
         my0 = tid < nc ? sm.off[tid] - base : 0ull;
     }
-    const uint32_t window = t_out ? FLAT_WINDOW / 2 : FLAT_WINDOW;
+    constexpr uint32_t window = WITH_T ? FLAT_WINDOW / 2 : FLAT_WINDOW;
     float* const win_t = reinterpret_cast<float*>(sm.pts + FLAT_WINDOW / 2);
     float2* gout = out + base;
-    float* gt = t_out ? t_out + base : nullptr;
+    float* gt = WITH_T ? t_out + base : nullptr;
     bool resolved = !FUSED;
     float t = 0.0f;
     uint32_t k = 0u;
     for (unsigned long long w0 = 0; w0 < total; w0 += window) {
         const unsigned long long w1 = min(total, w0 + (unsigned long long)window);
-        // ---- phase A
-        while (k < cnt && my0 + k < w1) {
-            const bool last = k + 1u == cnt;
-            V2 pos = to;
-            float tt = 1.0f;
-            if (!last) {
-                t = t + step;
-                tt = t;
-                float u = t;
-                pos = a0 + a1 * u;
-                u = u * t;
-                pos = pos + a2 * u;
-                if (NPTS == 4) {
+        // ---- phase A: my points [my0 + k, my0 + cnt) that fall into the window [w0, w1).  The sample loop is branch-free
+        // (the exact endpoint is peeled off) and indexes the window with 32-bit arithmetic: a third of the instructions
+        // per point of the straightforward loop, which was what bound the kernel.
+        {
+            const unsigned long long pos0 = my0 + k, pend = min(my0 + (unsigned long long)cnt, w1);
+            if (k < cnt && pos0 < pend) {
+                const uint32_t i0 = (uint32_t)(pos0 - w0), nk = (uint32_t)(pend - pos0);
+                const bool has_last = k + nk == cnt;
+                const uint32_t ninter = has_last ? nk - 1u : nk;
+                float2* const wp = sm.pts + i0;
+                float* const wt = win_t + i0;
+#pragma unroll 4
+                for (uint32_t j = 0; j < ninter; ++j) {
+                    t = t + step;
+                    float u = t;
+                    V2 pos = a0 + a1 * u;
                     u = u * t;
-                    pos = pos + a3 * u;
+                    pos = pos + a2 * u;
+                    if (NPTS == 4) {
+                        u = u * t;
+                        pos = pos + a3 * u;
+                    }
+                    wp[j] = make_float2(pos.x, pos.y);
+                    if (WITH_T) wt[j] = t;
                 }
+                if (has_last) {
+                    wp[ninter] = make_float2(to.x, to.y);
+                    if (WITH_T) wt[ninter] = 1.0f;
+                }
+                k += nk;
             }
-            const uint32_t i = (uint32_t)(my0 + k - w0);
-            sm.pts[i] = make_float2(pos.x, pos.y);
-            if (t_out) win_t[i] = tt;
-            ++k;
         }
         if (FUSED && !resolved) {
             // the block's base: look-back by warp 0 (the first window is already computed), then offsets out
@@ -707,14 +721,24 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
                 return;
             }
             gout = out + base;
-            gt = t_out ? t_out + base : nullptr;
+            gt = WITH_T ? t_out + base : nullptr;
         }
         __syncthreads();
-        // ---- phase B
+        // ---- phase B: the window leaves the SM as 16-byte stores (two points each; the odd point in front of the first
+        // 16-byte boundary and the one behind the last go out on their own)
         const uint32_t wn = (uint32_t)(w1 - w0);
-        for (uint32_t i = tid; i < wn; i += FLAT_CURVES) {
-            __stcs(gout + w0 + i, sm.pts[i]);
-            if (t_out) __stcs(gt + w0 + i, win_t[i]);
+        {
+            float2* const g = gout + w0;
+            const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(g) >> 3) & 1u) & (wn ? 1u : 0u);
+            if (tid == 0 && head) __stcs(g, sm.pts[0]);
+            const uint32_t pairs = (wn - head) >> 1;
+            for (uint32_t i = tid; i < pairs; i += FLAT_CURVES) {
+                const float2 p0 = sm.pts[head + 2u * i], p1 = sm.pts[head + 2u * i + 1u];
+                __stcs(reinterpret_cast<float4*>(g + head) + i, make_float4(p0.x, p0.y, p1.x, p1.y));
+            }
+            if (tid == FLAT_CURVES - 1 && ((wn - head) & 1u)) __stcs(g + wn - 1u, sm.pts[wn - 1u]);
+            if (WITH_T)
+                for (uint32_t i = tid; i < wn; i += FLAT_CURVES) __stcs(gt + w0 + i, win_t[i]);
         }
         __syncthreads();
     }
@@ -1294,14 +1318,20 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
     if ((reinterpret_cast<uintptr_t>(d_points) | reinterpret_cast<uintptr_t>(d_ctrl)) & 7u) return LYON_ERR_INVALID_ARGUMENT;
     if (n == 0 || total == 0) return LYON_OK;
     const size_t smem = sizeof(FlatSmem<NPTS>);
-    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    k_flat_emit<NPTS, false><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(
-        d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
+    if (d_t) {
+        CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        k_flat_emit<NPTS, false, true><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(
+            d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
+    } else {
+        CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        k_flat_emit<NPTS, false, false><<<grid_for(n, FLAT_CURVES), FLAT_CURVES, smem, c->stream>>>(
+            d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
+    }
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return LYON_OK;
 }
-// One pass: count + look-back + emit into caller-kept buffers (see k_flat_emit<NPTS, true>).
+// One pass: count + look-back + emit into caller-kept buffers (see k_flat_emit<NPTS, FUSED = true, WITH_T>).
 template <int NPTS>
 int flatten_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, uint64_t* d_offsets, float* d_points,
                   uint64_t capacity, float* d_t, uint64_t* total) {
@@ -1319,10 +1349,12 @@ int flatten_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, 
     CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 8, c->stream));
     const size_t smem = sizeof(FlatSmem<NPTS>);
-    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     FlatFused fu{(unsigned long long*)d_offsets, capacity, d_ticket(c, 0), (uint64_t*)c->desc.p, d_totals(c)};
     if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
-    k_flat_emit<NPTS, true><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+    if (d_t) k_flat_emit<NPTS, true, true><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+    else k_flat_emit<NPTS, true, false><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
     if (c->timing) {
         CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
         c->ev_valid = true;
@@ -1531,6 +1563,7 @@ int tile_prepass(lyon_cuda_ctx* c, const lyon_path_batch* b, bool* usable, bool 
     // coarse block = what one thread packs: 32 tiles' worth of slots, fewer for small batches (the packing of a block is
     // sequential, and a batch of a few hundred tiles should still spread over many threads)
     unsigned long long qc = 32ull * cap;
+    if (const char* e = getenv("LYON_PACK_QC")) qc = (unsigned long long)std::max(2, atoi(e)) * cap;  // experiments
     if (total / 512ull < qc) qc = total / 512ull;
     if (qc < 2ull * cap) qc = 2ull * cap;
     const unsigned long long n_blocks64 = total / qc + 1ull;
@@ -1583,7 +1616,11 @@ int ends_launch(lyon_cuda_ctx* c, const TileArgs& a) {
 
 template <int NT, int MODE, int MINB>
 int tile_launch_nt(lyon_cuda_ctx* c, const TileArgs& a) {
-    const size_t smem = tile_smem_bytes(a.s_cap, a.w_v, a.w_t);
+    size_t smem = tile_smem_bytes(a.s_cap, a.w_v, a.w_t);
+#ifdef LYON_DEV_BUILD  // experiments: LYON_TILE_PERSM=1 pads the allocation so that a single CTA fits an SM
+    if (const char* e = getenv("LYON_TILE_PERSM"))
+        if (atoi(e) == 1 && smem < (size_t)c->max_smem_optin / 2 + 2048) smem = (size_t)c->max_smem_optin / 2 + 2048;
+#endif
     auto kern = k_stroke_tile<NT, MODE, MINB>;
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

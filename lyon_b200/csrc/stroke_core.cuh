@@ -81,8 +81,17 @@ struct Views {
 static const uint8_t TF_FS = 0x80, TF_END = 0x40, TF_BEGIN = 0x20, TF_CLOSE = 0x10, TF_FIRST = 0x08, TF_EVAL = 0x04, TF_CUBIC = 0x02,
                      TF_LAST = 0x01;
 // CTA tiles (TileViews) use two of the low bits for the merge filter: FLAGGED = the point MAY be within the merge distance of
-// its predecessor (written with the slot, never changed), DROPPED = the merge filter dropped it (tile_resolve_run).
+// its predecessor (written with the slot, never changed), DROPPED = the merge filter dropped it.  While the runs are being
+// resolved (tile_resolve_run) the dropped points are collected in `dropmask`, one bit per slot set with an atomic OR, so the
+// flag bytes stay read-only in that phase and its threads share nothing they write (compute-sanitizer racecheck clean);
+// tile_merge_dropped then copies the bits into the flag bytes, where every later phase reads them with the byte it loads
+// anyway.
 static const uint8_t TF_FLAGGED = 0x02, TF_DROPPED = 0x04;
+#ifdef __CUDA_ARCH__
+#define LYC_ATOMIC_OR_U32(ptr, v) atomicOr((ptr), (v))
+#else
+#define LYC_ATOMIC_OR_U32(ptr, v) (*(ptr) |= (v))
+#endif
 // One slot array of a CTA tile.  Under nvcc it is a 32-bit byte offset into the CTA's dynamic shared memory: the accessors
 // go through the `extern __shared__` symbol, so every access compiles to LDS / STS with 32-bit address arithmetic (a
 // pointer kept in a struct that is passed to out-of-line routines degrades to generic LD / ST with 64-bit address
@@ -138,6 +147,7 @@ struct TileViews {
     TArr<uint32_t> voff;
     TArr<uint32_t> toff;
     TArr<uint8_t> jcode;
+    TArr<uint32_t> dropmask;  // one bit per slot: dropped by the merge filter (until tile_merge_dropped)
     uint32_t n_slots;
     LYC_HD V2 P(uint32_t s) const { return pos[s]; }
     LYC_HD float A(uint32_t s) const { return adv[s]; }
@@ -694,6 +704,79 @@ struct EmitSinkWide : EmitSink {
 #endif
     }
 };
+
+// The sink of the tile kernels' dense join pass: the same bytes as EmitSink, in fewer and fuller store transactions (the
+// emit phases are bound by the SM's store path, which handles one 32-byte sector per transaction however little of it a
+// store fills).  A vertex is ONE 256-bit store; the three indices of a triangle (12 bytes, so every other triangle starts
+// off an 8-byte boundary) go out as 64-bit stores: the odd word waits in `pend` for the first index of the next triangle.
+// flush() writes a word that is still waiting; it must run before anybody else continues at idx + 3 * nt (arc()) and when
+// the slot is done.
+struct EmitSinkPacked : EmitSink {
+    uint32_t pend;
+    bool has_pend;
+#ifdef __CUDA_ARCH__
+    __device__ __forceinline__ uint32_t add_vertex(const VertexTemplate& vt, V2 normal, bool negative) {
+        const float srcbits = __uint_as_float((vt.src & 0x7FFFFFFFu) | (negative ? SIDE_NEG_BIT : 0u));
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(__cvta_generic_to_global(vtx + nv)),
+                     "f"(vt.position_on_path.x), "f"(vt.position_on_path.y), "f"(normal.x), "f"(normal.y), "f"(vt.advancement),
+                     "f"(vt.half_width), "f"(srcbits), "f"(vt.t)
+                     : "memory");
+        return base + nv++;
+    }
+    __device__ __forceinline__ void add_triangle(uint32_t a, uint32_t b, uint32_t c) {
+        uint32_t* d = idx + 3u * (size_t)nt;
+        if (has_pend) {  // the word in front of d is waiting, and it is 8-byte aligned
+            *reinterpret_cast<uint2*>(d - 1) = make_uint2(pend, a);
+            *reinterpret_cast<uint2*>(d + 1) = make_uint2(b, c);
+            has_pend = false;
+        } else if ((reinterpret_cast<uintptr_t>(d) & 7u) == 0u) {
+            *reinterpret_cast<uint2*>(d) = make_uint2(a, b);
+            pend = c;
+            has_pend = true;
+        } else {
+            d[0] = a;
+            *reinterpret_cast<uint2*>(d + 1) = make_uint2(b, c);
+        }
+        nt++;
+    }
+    __device__ __forceinline__ void flush() {
+        if (has_pend) idx[3u * (size_t)nt - 1u] = pend;
+        has_pend = false;
+    }
+    __device__ __forceinline__ void arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va, uint32_t vb,
+                                        uint32_t total);
+#else
+    LYC_HD void flush() {}
+#endif
+};
+#ifdef __CUDA_ARCH__
+// All vertices and triangles of one arc through the packed sink (one copy of this code per kernel).
+__device__ __noinline__ void arc_emit_packed_nl(GpuVertex* vtx, uint32_t* idx, uint32_t first_id, VertexTemplate vt, bool negative,
+                                                float a0, float a1, uint32_t va, uint32_t vb, uint32_t total) {
+    EmitSinkPacked s;
+    s.vtx = vtx;
+    s.idx = idx;
+    s.nv = s.nt = 0u;
+    s.base = first_id;
+    s.has_pend = false;
+    s.pend = 0u;
+    for (uint32_t j = 0; j < total; ++j) {
+        ArcNode n = arc_node(a0, a1, va, vb, total, first_id, j);
+        // (two 128-bit stores: in this out-of-line function ptxas 12.9 turned the 256-bit store into a 32-bit one in one
+        // of the kernel instantiations -- see EmitSinkWide)
+        s.EmitSink::add_vertex(vt, arc_normal(n.mid), negative);
+        s.add_triangle(n.ida, n.id, n.idb);
+    }
+    s.flush();
+}
+__device__ __forceinline__ void EmitSinkPacked::arc(const VertexTemplate& vt, bool negative, float a0, float a1, uint32_t va,
+                                                    uint32_t vb, uint32_t total) {
+    flush();
+    arc_emit_packed_nl(vtx + nv, idx + 3u * (size_t)nt, base + nv, vt, negative, a0, a1, va, vb, total);
+    nv += total;
+    nt += total;
+}
+#endif
 
 // stroke.rs:1869-1904.  (ids of p0 after its join, ids of p1 before its join, with the fold remaps)
 template <class Sink>

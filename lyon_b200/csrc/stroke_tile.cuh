@@ -487,7 +487,7 @@ LYC_HD void tile_path_walk(const W& w, const StrokeParams& p, uint32_t sa, uint3
 // sequential -- but only inside a RUN of consecutive flagged points: an unflagged point is certainly kept (it is further
 // than sqrt(5)x the merge distance from its predecessor, which in turn is within the merge distance of whatever point
 // is the last kept one), so the point before a run is kept whatever happened earlier.  One thread resolves one run, all
-// runs of the tile at once (tile kernel: a thread per slot looks for run starts): a dropped point gets TF_DROPPED and the
+// runs of the tile at once (tile kernel: a thread per slot looks for run starts): a dropped point gets its bit in `dropmask` and the
 // length -0.0f (adv + -0.0f == adv: the advancement chain then needs no branch), a kept one the distance to the last kept
 // point; the unflagged point right after a dropped one is re-measured against the last kept point as the reference does
 // (last_kept != s - 1).  `s` must be a run start: flagged, its predecessor not flagged (an ordinary point or a Begin).
@@ -511,7 +511,7 @@ LYC_HD void tile_resolve_run(const W& w, const StrokeParams& p, uint32_t s, uint
         if (r != s && !((flagged && prev_flagged) || last_kept != r - 1u)) break;
         const V2 pl = w.pos[last_kept], ps = w.pos[r];
         if (sqlen(pl - ps) < p.merge_thr) {
-            w.flags[r] = (uint8_t)(fl | TF_DROPPED);
+            LYC_ATOMIC_OR_U32(&w.dropmask[r >> 5], 1u << (r & 31u));
             len[r] = -0.0f;
         } else {
             len[r] = length(ps - pl);
@@ -519,6 +519,13 @@ LYC_HD void tile_resolve_run(const W& w, const StrokeParams& p, uint32_t s, uint
         }
         prev_flagged = flagged;
     }
+}
+
+// After the runs: the dropped bit of slot s moves from the mask into its flag byte (thread per slot; a warp of 32
+// consecutive slots shares one mask word and mostly finds it empty).
+template <class W>
+LYC_HD void tile_merge_dropped(const W& w, uint32_t s) {
+    if ((w.dropmask[s >> 5] >> (s & 31u)) & 1u) w.flags[s] = (uint8_t)(w.flags[s] | TF_DROPPED);
 }
 
 // The sub-path record of End slot `e` (written by the verb phase with the Begin slot and the closed bit) gets what depends on
@@ -531,8 +538,8 @@ LYC_HD void tile_end_record_finish(const W& w, uint32_t e) {
     const bool close = (f2u(rec.y) & REC_CLOSE) != 0u;
     uint32_t m = (b0 < e && (w.flags[b0] & TF_BEGIN)) ? 1u : 0u;
     for (uint32_t r = b0 + 1u; r < e && m < 3u && m >= 1u; ++r)
-        if (!(w.flags[r] & (TF_DROPPED | TF_BEGIN | TF_END))) ++m;
-    bool mnec = m >= 1u && b0 + 1u < e && (w.flags[b0 + 1u] & TF_DROPPED) != 0;
+        if (!(w.flags[r] & (TF_BEGIN | TF_END)) && !w.D(r)) ++m;
+    bool mnec = m >= 1u && b0 + 1u < e && w.D(b0 + 1u);
     if (close && m == 1u) mnec = true;
     rec.y = u2f(m | (mnec ? REC_MNEC : 0u) | (close ? REC_CLOSE : 0u));
     w.pos[e] = rec;

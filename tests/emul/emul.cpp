@@ -164,6 +164,8 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     w.voff = voff.data();
     w.toff = toff.data();
     w.jcode = jcode.data();
+    std::vector<uint32_t> dropmask(NS / 32 + 2, 0u);
+    w.dropmask = dropmask.data();
     w.n_slots = NS;
     // phase 1a: slots of every verb (curves: accumulated t only); EndpointIds per path
     std::vector<uint32_t> verb_path(NV, 0), evt_before(NV + 1, 0);
@@ -190,6 +192,7 @@ extern "C" int emul_stroke_batch_tile(const lyon_path_batch* b, const lyon_strok
     for (uint32_t pass = 0; pass < 2u; ++pass)
         for (uint32_t s = 0; s < NS; ++s)
             if ((s & 1u) != pass && tile_run_start(w, s)) tile_resolve_run(w, p, s, NS);
+    for (uint32_t s = 0; s < NS; ++s) tile_merge_dropped(w, s);
     // phase 3: classify + count
     std::vector<uint32_t> cnt_v(NS + 1, 0), cnt_t(NS + 1, 0);
     for (uint32_t s = 0; s < NS; ++s) {

@@ -7,7 +7,9 @@ register octet -- only the first word of the vertex reached memory.  The wide st
 EmitSinkWide, for the fast joins (inlined into the tile kernels), and this script proves, for the .so that ships, that
   * every stroke tile kernel that emits contains its two STG.E.ENL2.256 instructions (one per fast-join vertex), and
   * no predicated 32-bit STG is paired with the 128-bit stores of the narrow path (the miscompile's signature when the
-    choice between the two was still made at run time).
+    choice between the two was still made at run time), and
+  * the EMIT and FUSED instantiations of a tile geometry hold the same number of them (fast joins: 2, the dense join
+    pass's EmitSinkPacked: the base vertices of a join).
 Usage: tools/check_sass.py [lib.so]   (exit code 1 on a violation; prints a short report)
 """
 import re
@@ -58,6 +60,18 @@ def main():
         print("MISCOMPILED wide store in", f, "\n   ", a, "\n   ", b)
     # the fast-join pass writes two vertices: two wide stores per emitting instantiation, none lost to the miscompile
     ok = bool(emitters) and not bad and all(n >= 2 for n in emitters.values())
+    # The EMIT and FUSED instantiations of one tile geometry compile the same emit code: a wide store that one of them
+    # lost (the miscompile seen in an out-of-line arc emitter: STG.E.ENL2.256 in one, a 32-bit STG.E in the other) shows up
+    # as different counts.
+    groups = {}
+    for f, n in emitters.items():
+        m = re.search(r"k_stroke_tileILi(\d+)ELi([12])ELi(\d+)E", f)
+        if m:
+            groups.setdefault((m.group(1), m.group(3)), {})[m.group(2)] = n
+    for key, modes in sorted(groups.items()):
+        if len(set(modes.values())) > 1:
+            print(f"MISMATCH: k_stroke_tile<{key[0]}, *, {key[1]}> has {modes} 256-bit stores in EMIT / FUSED")
+            ok = False
     print("check_sass:", "ok" if ok else "FAILED")
     return 0 if ok else 1
 
