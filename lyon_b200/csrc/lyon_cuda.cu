@@ -570,8 +570,8 @@ __global__ void __launch_bounds__(BLOCK) k_flat_count(const float* __restrict__ 
 //   phase B  thread / point   the window leaves the SM as contiguous 8-byte stores (a warp = 256 contiguous bytes).
 // HBM traffic: control points and offsets once, every output point once.
 #ifndef LYON_FLAT_CURVES
-#define LYON_FLAT_CURVES 256
-#define LYON_FLAT_WINDOW 8192
+#define LYON_FLAT_CURVES 128   // measured on C2 (10 M cubics): 256 / 8192: 0.83 ms, 128 / 3584: 0.72 ms, 64 / 1792: 0.76 ms
+#define LYON_FLAT_WINDOW 3584
 #endif
 constexpr int FLAT_CURVES = LYON_FLAT_CURVES;
 constexpr int FLAT_WINDOW = LYON_FLAT_WINDOW;  // points per window (half of it when the curve parameters are written too)
@@ -741,6 +741,160 @@ __global__ void __launch_bounds__(FLAT_CURVES) k_flat_emit(const float* __restri
                 for (uint32_t i = tid; i < wn; i += FLAT_CURVES) __stcs(gt + w0 + i, win_t[i]);
         }
         __syncthreads();
+    }
+}
+
+// The same emit pass with WARP-owned tiles (experiment, LYON_FLAT=warp): a warp owns 32 consecutive curves and a window of
+// its own, so nothing in the kernel is block-wide -- k_flat_emit spends a third of its warp time in the two block barriers
+// of every window.  FUSED: a warp takes a ticket, scans its 32 counts with shuffles, publishes the total, computes its
+// first window and only then resolves its base by decoupled look-back over the warp totals (one descriptor per 32
+// curves).  Measured on C2: 0.88 ms (640-point windows) against 0.72 ms for the block tiles -- eight times the tickets
+// and look-backs cost more than the barriers; the scattered window stores of phase A (bank conflicts) are the same.
+constexpr int FLATW_WARPS = 4;        // warps per block (the block is only a container)
+#ifndef LYON_FLATW_WINDOW
+#define LYON_FLATW_WINDOW 640
+#endif
+constexpr int FLATW_WINDOW = LYON_FLATW_WINDOW;  // points per warp window (half of it when the curve parameters are written too)
+template <int NPTS, bool FUSED, bool WITH_T>
+__global__ void __launch_bounds__(FLATW_WARPS * 32) k_flat_emit_w(const float* __restrict__ ctrl, unsigned long long n, float tol,
+                                                                 const unsigned long long* __restrict__ offsets,
+                                                                 float2* __restrict__ out, float* __restrict__ t_out, FlatFused fu) {
+    __shared__ __align__(16) float2 s_win[FLATW_WARPS][FLATW_WINDOW];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    float2* const win = s_win[wid];
+    uint32_t tile = blockIdx.x * FLATW_WARPS + wid;
+    if (FUSED) {
+        if (lane == 0u) tile = atomicAdd(fu.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+    const unsigned long long c0 = (unsigned long long)tile * 32ull;
+    if (c0 >= n) return;
+    const uint32_t nc = (uint32_t)min(32ull, n - c0);
+    // the warp's control points (nc * NPTS * 8 contiguous bytes) through its window: coalesced 4-byte loads
+    static_assert(FLATW_WINDOW * 2 >= 32 * 2 * NPTS, "window too small to stage the control points");
+    float* const stage = reinterpret_cast<float*>(win);
+    for (uint32_t i = lane; i < nc * 2u * NPTS; i += 32u) stage[i] = ctrl[c0 * 2ull * NPTS + i];
+    __syncwarp();
+    float step = 0.0f;
+    uint32_t cnt = 0u;
+    V2 a0 = v2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0, to = a0;
+    if (lane < nc) {
+        const float* c = stage + lane * 2u * NPTS;
+        float nseg;
+        if (NPTS == 4) {
+            const V2 from = v2(c[0], c[1]), c1 = v2(c[2], c[3]), c2 = v2(c[4], c[5]);
+            to = v2(c[6], c[7]);
+            nseg = cubic_wang(from, c1, c2, to, tol);
+            const CubicPoly q = cubic_poly(from, c1, c2, to);
+            a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3;
+        } else {
+            const V2 from = v2(c[0], c[1]), cc = v2(c[2], c[3]);
+            to = v2(c[4], c[5]);
+            nseg = quad_wang(from, cc, to, tol);
+            const QuadPoly q = quad_poly(from, cc, to);
+            a0 = q.a0; a1 = q.a1; a2 = q.a2;
+        }
+        step = 1.0f / nseg;
+        cnt = to_u32_or_1(nseg);
+    }
+    __syncwarp();  // `stage` (= the window) is free again
+    unsigned long long base = 0ull, total = 0ull, my0 = 0ull;  // my0: warp-relative index of my first point
+    if (FUSED) {
+        unsigned long long inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += y;
+        }
+        total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0u) lookback_publish(fu.desc, tile, total);
+        my0 = inc - cnt;
+    } else {
+        const unsigned long long o0 = offsets[c0], o1 = offsets[c0 + nc];
+        base = o0;
+        total = o1 - o0;
+        my0 = lane < nc ? offsets[c0 + lane] - o0 : 0ull;
+    }
+    constexpr uint32_t window = WITH_T ? FLATW_WINDOW / 2 : FLATW_WINDOW;
+    float* const win_t = reinterpret_cast<float*>(win + FLATW_WINDOW / 2);
+    float2* gout = out + base;
+    float* gt = WITH_T ? t_out + base : nullptr;
+    bool resolved = !FUSED;
+    float t = 0.0f;
+    uint32_t k = 0u;
+    for (unsigned long long w0 = 0; w0 < total; w0 += window) {
+        const unsigned long long w1 = min(total, w0 + (unsigned long long)window);
+        {  // ---- phase A (lane / curve): my points that fall into the window [w0, w1)
+            const unsigned long long pos0 = my0 + k, pend = min(my0 + (unsigned long long)cnt, w1);
+            if (k < cnt && pos0 < pend) {
+                const uint32_t i0 = (uint32_t)(pos0 - w0), nk = (uint32_t)(pend - pos0);
+                const bool has_last = k + nk == cnt;
+                const uint32_t ninter = has_last ? nk - 1u : nk;
+                float2* const wp = win + i0;
+                float* const wt = win_t + i0;
+#pragma unroll 4
+                for (uint32_t j = 0; j < ninter; ++j) {
+                    t = t + step;
+                    float u = t;
+                    V2 pos = a0 + a1 * u;
+                    u = u * t;
+                    pos = pos + a2 * u;
+                    if (NPTS == 4) {
+                        u = u * t;
+                        pos = pos + a3 * u;
+                    }
+                    wp[j] = make_float2(pos.x, pos.y);
+                    if (WITH_T) wt[j] = t;
+                }
+                if (has_last) {
+                    wp[ninter] = make_float2(to.x, to.y);
+                    if (WITH_T) wt[ninter] = 1.0f;
+                }
+                k += nk;
+            }
+        }
+        if (FUSED && !resolved) {
+            base = lookback_exclusive(fu.desc, tile, total, true);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            resolved = true;
+            if (lane < nc) fu.offsets_out[c0 + lane] = base + my0;
+            if (lane == nc - 1u && c0 + nc == n) {
+                fu.offsets_out[n] = base + total;
+                fu.totals->flat_points = base + total;
+            }
+            if (base + total > fu.capacity) {
+                if (lane == 0u) atomicOr(&fu.totals->error, 0x100u);  // point buffer too small: counted, not emitted
+                return;
+            }
+            gout = out + base;
+            gt = WITH_T ? t_out + base : nullptr;
+        }
+        __syncwarp();
+        // ---- phase B (lane / two points): the window leaves the SM as 16-byte stores, 512 contiguous bytes per instruction
+        const uint32_t wn = (uint32_t)(w1 - w0);
+        {
+            float2* const g = gout + w0;
+            const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(g) >> 3) & 1u) & (wn ? 1u : 0u);
+            if (lane == 0u && head) __stcs(g, win[0]);
+            const uint32_t pairs = (wn - head) >> 1;
+            for (uint32_t i = lane; i < pairs; i += 32u) {
+                const float2 p0 = win[head + 2u * i], p1 = win[head + 2u * i + 1u];
+                __stcs(reinterpret_cast<float4*>(g + head) + i, make_float4(p0.x, p0.y, p1.x, p1.y));
+            }
+            if (lane == 31u && ((wn - head) & 1u)) __stcs(g + wn - 1u, win[wn - 1u]);
+            if (WITH_T)
+                for (uint32_t i = lane; i < wn; i += 32u) __stcs(gt + w0 + i, win_t[i]);
+        }
+        __syncwarp();
+    }
+    if (FUSED && !resolved) {  // (a warp without points cannot happen: every curve has at least one; kept for safety)
+        base = lookback_exclusive(fu.desc, tile, total, true);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nc) fu.offsets_out[c0 + lane] = base + my0;
+        if (lane == nc - 1u && c0 + nc == n) {
+            fu.offsets_out[n] = base + total;
+            fu.totals->flat_points = base + total;
+        }
     }
 }
 
@@ -1193,6 +1347,7 @@ struct lyon_cuda_ctx {
     bool tile_has_split_recs = false;  // the pre-pass kept the plan of every split quadratic
     int wt_warps = 0;             // warps per CTA (= tiles in flight per SM)
     uint32_t wt_s_cap = 0, wt_v_cap = 0, wt_p_cap = 0, wt_bytes = 0;
+    bool flat_block_tiles = true;  // LYON_FLAT=warp: the warp-tile flatten kernel (k_flat_emit_w; measured slower) instead of block tiles
     int wt_mode = 0;              // 1 (LYON_PIPE=wtile / set_pipeline 3): warp tiles whenever they fit; 0: CTA tiles
     TileTotals* h_tile_totals = nullptr;  // pinned
     bool tile_planned = false;            // the last plan went through the tile pipeline
@@ -1317,6 +1472,18 @@ int flatten_emit(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, c
     if (!c || (n && (!d_ctrl || !d_offsets)) || (total && !d_points)) return LYON_ERR_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(d_points) | reinterpret_cast<uintptr_t>(d_ctrl)) & 7u) return LYON_ERR_INVALID_ARGUMENT;
     if (n == 0 || total == 0) return LYON_OK;
+    if (!c->flat_block_tiles) {  // warp-owned tiles (experiment)
+        const unsigned blocks = grid_for(n, 32 * FLATW_WARPS);
+        if (d_t)
+            k_flat_emit_w<NPTS, false, true><<<blocks, FLATW_WARPS * 32, 0, c->stream>>>(
+                d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
+        else
+            k_flat_emit_w<NPTS, false, false><<<blocks, FLATW_WARPS * 32, 0, c->stream>>>(
+                d_ctrl, n, tol, (const unsigned long long*)d_offsets, (float2*)d_points, d_t, FlatFused{});
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        return LYON_OK;
+    }
     const size_t smem = sizeof(FlatSmem<NPTS>);
     if (d_t) {
         CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
@@ -1343,17 +1510,24 @@ int flatten_fused(lyon_cuda_ctx* c, const float* d_ctrl, uint64_t n, float tol, 
         if (d_offsets) CU_TRY(c, cudaMemsetAsync(d_offsets, 0, 8, c->stream));
         return LYON_OK;
     }
-    const unsigned tiles = grid_for(n, FLAT_CURVES);
+    const bool wtiles = !c->flat_block_tiles;  // warp-owned tiles (experiment): one look-back descriptor per 32 curves
+    const unsigned tiles = wtiles ? grid_for(n, 32) : grid_for(n, FLAT_CURVES);
     TRY(ensure(c, c->misc, 512));
     TRY(ensure(c, c->desc, (size_t)tiles * 8));
     CU_TRY(c, cudaMemsetAsync(c->misc.p, 0, 512, c->stream));
     CU_TRY(c, cudaMemsetAsync(c->desc.p, 0, (size_t)tiles * 8, c->stream));
     const size_t smem = sizeof(FlatSmem<NPTS>);
-    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    if (!wtiles) {
+        CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        CU_TRY(c, (cudaFuncSetAttribute(k_flat_emit<NPTS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    }
     FlatFused fu{(unsigned long long*)d_offsets, capacity, d_ticket(c, 0), (uint64_t*)c->desc.p, d_totals(c)};
     if (c->timing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
-    if (d_t) k_flat_emit<NPTS, true, true><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+    if (wtiles) {
+        const unsigned blocks = grid_for(n, 32 * FLATW_WARPS);
+        if (d_t) k_flat_emit_w<NPTS, true, true><<<blocks, FLATW_WARPS * 32, 0, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+        else k_flat_emit_w<NPTS, true, false><<<blocks, FLATW_WARPS * 32, 0, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
+    } else if (d_t) k_flat_emit<NPTS, true, true><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
     else k_flat_emit<NPTS, true, false><<<tiles, FLAT_CURVES, smem, c->stream>>>(d_ctrl, n, tol, nullptr, (float2*)d_points, d_t, fu);
     if (c->timing) {
         CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
@@ -1850,6 +2024,7 @@ int lyon_cuda_create(int device, void* stream, lyon_cuda_ctx** out) {
     lyon_cuda_ctx* c = new lyon_cuda_ctx();
     c->device = device;
     if (const char* e = getenv("LYON_PIPE")) c->wt_mode = strcmp(e, "wtile") == 0 ? 1 : 0;  // experiments: warp tiles
+    if (const char* e = getenv("LYON_FLAT")) c->flat_block_tiles = strcmp(e, "warp") != 0;  // experiments: warp-tile flatten
     c->stream = (cudaStream_t)stream;  // NULL is CUDA's default stream
     {
         cudaDeviceProp prop;
