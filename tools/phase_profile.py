@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import workloads as W  # noqa: E402
 from lyon_b200 import DeviceTessellator, LineCap, LineJoin, StrokeOptions  # noqa: E402
 
-NAMES_CTILE = ["0 ticket", "1a verbs", "1b eval", "1c special", "2 walk", "3 classify", "3 dense count", "4 scan", "5 lookback",
+NAMES_CTILE = ["0 header", "1a verbs + split", "1c merge filter", "-", "-", "3 classify", "3 dense count", "4 scan + chains", "5 lookback",
                "6 fast emit", "6 full/end emit", "0 stage (TMA wait)"]
 NAMES_WTILE = ["0 ticket+header", "0 stage (TMA)", "1 setup (verbs)", "2 gen (slots)", "3 walk", "4 classify", "4 dense count",
                "5 scan", "6 lookback", "7 fast emit", "7 full emit", "7 end records"]
@@ -45,6 +45,8 @@ def main():
     print(f"paths {n} vertices {v.shape[0]} kernel {ms:.3f} ms")
     for k, name in enumerate(names):
         print(f"  {name:18s} {out[k] / tot * 100:6.2f} %   {out[k]:>14d} cycles")
+    if names is NAMES_CTILE:
+        print("  tiles by number of non-fast joins: <=480 %d, <=512 %d, <=544 %d, >544 %d" % tuple(out[12:16]))
 
 
 if __name__ == "__main__":
