@@ -289,10 +289,10 @@ def main():
         "bound": "hbm", "kernel": "k_stroke_tile<FUSED>", "achieved": k_gbs,
         "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: `ncu --set full` on the first 200k paths of the same
-        # batch (profiles/r02_ncu_summary.txt) measured 8.526 GB written + 0.488 GB read = 9.014 GB for 8.686 GB of
+        # batch (profiles/r02_ncu_summary.txt) measured 8.449 GB written + 0.501 GB read = 8.951 GB for 8.686 GB of
         # algorithmic bytes.  ESTIMATE for this launch: that ratio times the launch's algorithmic bytes (a profiler cannot
         # run inside the timed region).
-        "traffic": int(alg_bytes * (9.014 / 8.686)), "traffic_source": "estimated: ncu ratio of a 200k-path sample x algorithmic bytes",
+        "traffic": int(alg_bytes * (8.951 / 8.686)), "traffic_source": "estimated: ncu ratio of a 200k-path sample x algorithmic bytes",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms": dev_ms / args.steps,
         "kernel_share_of_step": k_ms / (dev_ms / args.steps),
         "whole_step_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,

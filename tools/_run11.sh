@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-export LYON_CUDA_LIB=$PWD/lyon_b200/liblyon_cuda_pp.so
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/v05_tests.log 2>&1
-tail -2 gpurun_out/v05_tests.log
-{ tools/gpu_variants.sh pp d8 pp d8
-LYON_PREPASS=warp tools/gpu_variants.sh pp
-tools/gpu_variants.sh nt320:320,3520,0 nt288:288,3520,0 nt320:320,3520,0 nt288:288,3520,0
-} | tee gpurun_out/v05_variants.log
+export LYON_CUDA_LIB=$PWD/lyon_b200/liblyon_cuda_f2.so
+timeout 900 python -m pytest tests -m gpu -x -q -k "flatten or c2 or measure or abi" > gpurun_out/v06_tests.log 2>&1
+tail -3 gpurun_out/v06_tests.log
+{ for t in f2 f2w512 f2w512b6; do echo -n "$t: "; LYON_CUDA_LIB=$PWD/lyon_b200/liblyon_cuda_$t.so python tools/run_c2.py 2>&1 | tail -1; done
+echo -n "f2 block: "; LYON_FLAT=block LYON_CUDA_LIB=$PWD/lyon_b200/liblyon_cuda_f2.so python tools/run_c2.py 2>&1 | tail -1
+} | tee gpurun_out/v06_flat.log
