@@ -129,6 +129,36 @@ def test_edge_cases(tz):
     assert mc.positions()[:, 1].max() == np.float32(345.0)
 
 
+def test_verb_round_boundaries(tz):
+    """The verb phase and the pre-pass run a path's verbs in rounds of 32 with its first Begin and last End / Close set
+    aside: paths whose verb counts sit around the round boundaries (1 .. 3, 32 .. 35, 64 .. 68, 96 .. 99 verbs), single and
+    multiple sub-paths, open and closed, mixed segment kinds."""
+    rng = np.random.default_rng(77)
+    paths = []
+    for nseg in (0, 1, 2, 30, 31, 32, 33, 34, 62, 63, 64, 65, 66, 67, 94, 95, 96, 97):
+        for closed in (False, True):
+            b = Path.builder()
+            p0 = rng.uniform(-50, 50, 2)
+            b.begin((float(p0[0]), float(p0[1])))
+            for k in range(nseg):
+                q = rng.uniform(-50, 50, 6)
+                kind = (k + nseg) % 3
+                if kind == 0:
+                    b.line_to((float(q[0]), float(q[1])))
+                elif kind == 1:
+                    b.quadratic_bezier_to((float(q[0]), float(q[1])), (float(q[2]), float(q[3])))
+                else:
+                    b.cubic_bezier_to((float(q[0]), float(q[1])), (float(q[2]), float(q[3])), (float(q[4]), float(q[5])))
+            b.end(closed)
+            if nseg in (31, 64):  # a second sub-path: the set-aside End is not the only End
+                b.begin((1.0, 2.0)); b.line_to((3.0, 5.0)); b.line_to((-4.0, 1.0)); b.end(not closed)
+            paths.append(b.build())
+    batch = PathBatch.from_paths(paths)
+    for o in (StrokeOptions(line_width=2.0, line_join=LineJoin.Round, tolerance=0.1).with_line_cap(LineCap.Round),
+              StrokeOptions(line_width=1.0, line_join=LineJoin.MiterClip, tolerance=0.02).with_line_cap(LineCap.Square)):
+        assert_mesh_parity(gpu_stroke(tz, batch, o), O.stroke_batch(batch, o), bbox_extent(batch), what=str(o))
+
+
 def test_ragged_batch_and_tile_boundaries(tz):
     """Paths of very different sizes so that sub-paths straddle scan tiles (256 slots / 256 verbs)."""
     rng = np.random.default_rng(9)
