@@ -124,3 +124,71 @@ def test_packed_triangle_stores_write_every_index_once_in_order():
             assert np.all(buf[:start] == -1) and np.all(buf[start + 3 * k:] == -1)
             # three words in at most two stores per triangle, plus one flush word per batch at most
             assert len(stores) <= 2 * k + len(batches)
+
+
+def tile_end_bsearch(psb, p, hi, cap):
+    limit = psb[p] + cap
+    a, b = p + 1, hi + 1
+    while a < b:
+        mid = a + ((b - a) >> 1)
+        if psb[mid] <= limit:
+            a = mid + 1
+        else:
+            b = mid
+    return a - 1
+
+
+def tile_end_walk(psb, p, hi, cap, est):
+    """k_tile_pack: start from the previous tile's path count, walk at most eight steps, then the binary search."""
+    limit = psb[p] + cap
+    a, b = p + 1, hi + 1
+    g = min(p + est, hi)
+    if psb[g] <= limit:
+        a = g + 1
+        k = 0
+        while k < 8 and a < b and psb[a] <= limit:
+            a += 1
+            k += 1
+        if a < b and psb[a] > limit:
+            b = a
+    else:
+        b = g
+        k = 0
+        while k < 8 and a < b and psb[b - 1] > limit:
+            b -= 1
+            k += 1
+        if a < b and psb[b - 1] <= limit:
+            a = b
+    while a < b:
+        mid = a + ((b - a) >> 1)
+        if psb[mid] <= limit:
+            a = mid + 1
+        else:
+            b = mid
+    return a - 1
+
+
+def test_tile_packer_walk_finds_the_same_tile_ends_as_the_binary_search():
+    rng = np.random.default_rng(13)
+    for trial in range(200):
+        n = int(rng.integers(1, 400))
+        kind = trial % 4
+        if kind == 0:
+            sizes = rng.integers(1, 50, n)
+        elif kind == 1:
+            sizes = rng.integers(380, 440, n)            # C3-like: ~410 slots per path
+        elif kind == 2:
+            sizes = np.where(rng.random(n) < 0.05, rng.integers(2000, 5000, n), rng.integers(1, 20, n))
+        else:
+            sizes = rng.integers(0, 3, n)                # empty paths
+        psb = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        cap = int(rng.choice([64, 512, 3520]))
+        hi = n
+        p, est = 0, int(rng.integers(1, 40))
+        while p < hi:
+            want = tile_end_bsearch(psb, p, hi, cap)
+            got = tile_end_walk(psb, p, hi, cap, max(1, est))
+            assert got == want, (trial, p, est)
+            q = max(want, p + 1)  # a path longer than the capacity is a tile of its own
+            est = q - p
+            p = q
