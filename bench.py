@@ -278,7 +278,7 @@ def main():
     total_i = sum_over_ranks(ni)
     value = total_v / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (k_stroke_tile: FUSED at N=1, EMIT at N>1), timed by CUDA events the library
+    # roofline of the dominant kernel (k_stroke_tile<FUSED>, at every N: the sharded entry runs the same single pass), timed by CUDA events the library
     # records around that launch on its stream.  Algorithmic bytes = inputs read once + every vertex and index written once.
     peak, peak_src = measured_peaks()
     in_bytes = dbatch.input_bytes()
